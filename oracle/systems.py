@@ -1,0 +1,197 @@
+"""CPU oracle: the reference's control systems, restated.
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product (myriad_b200/) never
+imports it.  Parity status: pinned against the reference's own Python code executed under
+oracle/refshim (see oracle/make_golden.py -> tests/golden/*.npz); solver arithmetic of IPOPT
+itself is un-vendored, hence "solver-output parity unpinned vs IPOPT" (DESIGN.md).
+
+Every function broadcasts over leading batch dimensions: ``x[..., n]``, ``u[..., m]`` and
+works for NumPy (real or complex -- used for complex-step derivatives) and torch tensors
+(used for torch.func Hessians).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+try:  # torch is optional for the oracle (only second derivatives need it)
+  import torch
+except Exception:  # pragma: no cover
+  torch = None
+
+
+def _xp(a):
+  if torch is not None and isinstance(a, torch.Tensor):
+    return torch
+  return np
+
+
+def _stack(xs, like):
+  xp = _xp(like)
+  return xp.stack(list(xs), -1) if xp is np else torch.stack(list(xs), dim=-1)
+
+
+@dataclass
+class OracleSystem:
+  """Mirror of FiniteHorizonControlSystem (myriad/systems/base.py:11-111)."""
+  name: str
+  x_0: np.ndarray
+  x_T: Optional[Sequence]  # entries may be None (myriad/systems/lenhart/predator_prey.py:56)
+  T: float
+  bounds: np.ndarray  # (n+m, 2): states first, then controls (simple_case.py:30-33)
+  terminal_cost: bool = False
+  params: dict = field(default_factory=dict)
+
+  @property
+  def n(self):
+    return self.x_0.shape[0]
+
+  @property
+  def m(self):
+    return self.bounds.shape[0] - self.n
+
+  def dynamics(self, x, u):
+    raise NotImplementedError
+
+  def cost(self, x, u, t):
+    raise NotImplementedError
+
+  def terminal_cost_fn(self, x, u):  # base.py:101-111
+    return 0.0
+
+
+class SimpleCase(OracleSystem):
+  """myriad/systems/lenhart/simple_case.py:25-53"""
+
+  def __init__(self, A=1., B=1., C=4., x_0=1., T=1.):
+    super().__init__("SIMPLECASE", np.array([x_0]), None, T,
+                     np.array([[-np.inf, np.inf], [-np.inf, np.inf]]), False,
+                     dict(A=A, B=B, C=C))
+
+  def dynamics(self, x, u):
+    C = self.params["C"]
+    return _stack([-0.5 * x[..., 0] ** 2 + C * u[..., 0]], x)  # simple_case.py:48
+
+  def cost(self, x, u, t):
+    A, B = self.params["A"], self.params["B"]
+    return -A * x[..., 0] + B * u[..., 0] ** 2  # simple_case.py:53
+
+
+class CartPole(OracleSystem):
+  """myriad/systems/classical_control/cartpole.py:50-108 (dynamics follow the CODE, :76-87,
+  not the docstring at :28 -- SURVEY.md section 9-1)."""
+
+  def __init__(self, g=9.81, m1=1., m2=.3, length=0.5):
+    super().__init__("CARTPOLE", np.zeros(4), np.array([1.0, np.pi, 0., 0.]), 2.0,
+                     np.array([[-2., 2.], [-2 * np.pi, 2 * np.pi], [-5., 5.], [-10., 10.],
+                               [-20., 20.]]), False, dict(g=g, m1=m1, m2=m2, length=length))
+
+  def dynamics(self, x, u):
+    xp = _xp(x)
+    p = self.params
+    g, m1, m2, l = p["g"], p["m1"], p["m2"], p["length"]
+    theta, dx, dtheta = x[..., 1], x[..., 2], x[..., 3]
+    u0 = u[..., 0]
+    s, c = xp.sin(theta), xp.cos(theta)
+    ddx = ((l * m2 * s * dtheta ** 2 + u0 + m2 * g * c * s)
+           / (m1 + m2 * (1 - c ** 2)))  # cartpole.py:79-80
+    ddtheta = -((l * m2 * c * dtheta ** 2 + u0 * c + (m1 + m2) * g * s)
+                / (l * m1 + l * m2 * (1 - c ** 2)))  # cartpole.py:83-85
+    return _stack([dx, dtheta, ddx, ddtheta], x)
+
+  def cost(self, x, u, t):
+    return u[..., 0] ** 2  # cartpole.py:108
+
+
+class VanDerPol(OracleSystem):
+  """myriad/systems/miscellaneous/van_der_pol.py:29-60"""
+
+  def __init__(self, a=1.):
+    super().__init__("VANDERPOL", np.array([0., 1.]), np.zeros(2), 10.0,
+                     np.array([[-4., 4.], [-4., 4.], [-0.75, 1.0]]), False, dict(a=a))
+
+  def dynamics(self, x, u):
+    a = self.params["a"]
+    x0, x1 = x[..., 0], x[..., 1]
+    return _stack([a * (1. - x1 ** 2) * x0 - x1 + u[..., 0], x0], x)  # van_der_pol.py:48-50
+
+  def cost(self, x, u, t):
+    return x[..., 0] ** 2 + x[..., 1] ** 2 + u[..., 0] ** 2  # van_der_pol.py:60 (x.T @ x + u**2)
+
+
+class CancerTreatment(OracleSystem):
+  """myriad/systems/lenhart/cancer_treatment.py:40-76"""
+
+  def __init__(self, r=0.3, a=3., delta=0.45, x_0=0.975, T=20):
+    super().__init__("CANCERTREATMENT", np.array([x_0]), None, T,
+                     np.array([[1e-3, 1.], [0., 2.]]), False, dict(r=r, a=a, delta=delta))
+
+  def dynamics(self, x, u):
+    xp = _xp(x)
+    r, delta = self.params["r"], self.params["delta"]
+    x0 = x[..., 0]
+    return _stack([r * x0 * xp.log(1 / x0) - u[..., 0] * delta * x0], x)  # cancer_treatment.py:64
+
+  def cost(self, x, u, t):
+    return self.params["a"] * x[..., 0] ** 2 + u[..., 0] ** 2  # cancer_treatment.py:76
+
+
+class NodeSystem(OracleSystem):
+  """NODE-dynamics wrapper: myriad/systems/neural_ode/node_system.py:14-42 with the MLP of
+  myriad/neural_ode/create_node.py:110-117 (hk.Linear = x @ w + b, sigmoid between layers).
+  ``weights`` is a list of (w:(in,out), b:(out,)) in layer order (haiku keys linear, linear_1, ...)."""
+
+  def __init__(self, true_system: OracleSystem, weights):
+    super().__init__("NODE_" + true_system.name, true_system.x_0, true_system.x_T, true_system.T,
+                     true_system.bounds, true_system.terminal_cost, {})
+    self.true_system = true_system
+    self.weights = [(np.asarray(w, dtype=np.float64), np.asarray(b, dtype=np.float64)) for w, b in weights]
+
+  def dynamics(self, x, u):
+    xp = _xp(x)
+    if xp is np:
+      h = np.concatenate([x, u], axis=-1)  # jnp.append(x_t, u_t), node_system.py:37
+      for i, (w, b) in enumerate(self.weights):
+        h = h @ w + b
+        if i + 1 < len(self.weights):
+          h = 1.0 / (1.0 + np.exp(-h))
+      return h
+    h = torch.cat([x, u], dim=-1)
+    for i, (w, b) in enumerate(self.weights):
+      h = h @ torch.as_tensor(w) + torch.as_tensor(b)
+      if i + 1 < len(self.weights):
+        h = torch.sigmoid(h)
+    return h
+
+  def cost(self, x, u, t):
+    return self.true_system.cost(x, u, t)  # node_system.py:41-42
+
+
+def haiku_style_mlp_weights(n_in: int, hidden: Sequence[int], n_out: int, seed: int = 42):
+  """Synthetic MLP weights with haiku's default Linear init (truncated normal, stddev 1/sqrt(fan_in),
+  zero bias), drawn with numpy's PCG64 so they are reproducible without jax."""
+  rng = np.random.Generator(np.random.PCG64(seed))
+  sizes = [n_in] + list(hidden) + [n_out]
+  out = []
+  for fi, fo in zip(sizes[:-1], sizes[1:]):
+    std = 1.0 / math.sqrt(fi)
+    w = rng.standard_normal((fi, fo))
+    w = np.clip(w, -2.0, 2.0) * std
+    out.append((w, np.zeros(fo)))
+  return out
+
+
+SYSTEMS = {
+  "SIMPLECASE": SimpleCase,
+  "CARTPOLE": CartPole,
+  "VANDERPOL": VanDerPol,
+  "CANCERTREATMENT": CancerTreatment,
+}
+
+
+def make_system(name: str, **params) -> OracleSystem:
+  return SYSTEMS[name](**params)
