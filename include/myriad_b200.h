@@ -1,0 +1,171 @@
+/* myriad_b200 -- C ABI of the B200-native batched trajectory-optimization engine.
+ *
+ * The reference (nikihowe/myriad) has no native FFI: its hot path is Python calling XLA and
+ * cyipopt.  These entry points are what a binding for that path binds
+ * instead; each comment names the reference interface the call replaces.  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every array is contiguous fp64 (or int32) and OWNED BY THE CALLER;
+ *    device entry points take DEVICE pointers (e.g. torch.Tensor.data_ptr()) and a cudaStream_t passed
+ *    as void*; the library never allocates or frees device memory (the workspace is passed in).
+ *  - all batched arrays are instance-major: [B][...].
+ *  - decision vector layout == the reference's ravel_pytree((x, u)): all states time-major, then all
+ *    controls time-major (shooting.py:75, trapezoidal.py:51, hermite_simpson.py:47); constraint vector
+ *    layout and SIGN conventions == the reference's constraints() of the same transcription.
+ *  - every function returns 0 on success or a negative MYR_E_* code; myr_last_error() gives the
+ *    thread-local message.  Nothing throws across the ABI.  Work is enqueued asynchronously on
+ *    the given stream; the caller synchronises.
+ *  - myr_host_* are single-threaded CPU builds of the same templates taking HOST pointers.  They
+ *    exist for debugging / CI without a GPU; the Python product path never calls them.
+ */
+#ifndef MYRIAD_B200_H
+#define MYRIAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MYR_ABI_VERSION 1
+#define MYR_MAX_PARAMS 16
+
+/* SystemType members with a device implementation (myriad/systems/__init__.py:29-50). */
+enum {
+  MYR_SYS_SIMPLECASE = 0,
+  MYR_SYS_CARTPOLE = 1,
+  MYR_SYS_VANDERPOL = 2,
+  MYR_SYS_CANCERTREATMENT = 3,
+  MYR_SYS_MOULDFUNGICIDE = 4,
+  MYR_SYS_BIOREACTOR = 5,
+  MYR_SYS_SIMPLECASEWITHBOUNDS = 6,
+  MYR_SYS_GLUCOSE = 7,
+  MYR_SYS_HARVEST = 8,
+  MYR_SYS_TIMBERHARVEST = 9
+};
+/* OptimizerType x QuadratureRule (myriad/config.py:12-17,53-56; get_optimizer, trajectory_optimizers/__init__.py:12-28) */
+enum { MYR_OPT_SHOOTING = 0, MYR_OPT_TRAPEZOIDAL = 1, MYR_OPT_HERMITE_SIMPSON = 2 };
+/* IntegrationMethod (myriad/config.py:46-50) */
+enum { MYR_INT_EULER = 0, MYR_INT_HEUN = 1, MYR_INT_MIDPOINT = 2, MYR_INT_RK4 = 3 };
+
+enum {
+  MYR_OK = 0,
+  MYR_E_BADARG = -1,      /* unknown enum / inconsistent sizes: the reference raises KeyError / ValueError */
+  MYR_E_UNSUPPORTED = -2, /* combination without a kernel yet */
+  MYR_E_CUDA = -3,        /* a CUDA call failed */
+  MYR_E_WORKSPACE = -4    /* workspace too small */
+};
+
+/* Per-instance solver exit codes written to status_out (IPOPT-style; the reference only reads
+ * success == (status == 0), myriad/nlp_solvers/__init__.py:64). */
+enum {
+  MYR_ST_SOLVED = 0,
+  MYR_ST_ACCEPTABLE = 1,
+  MYR_ST_MAXITER = -1,
+  MYR_ST_LINESEARCH = -2,
+  MYR_ST_INERTIA = -3,
+  MYR_ST_NAN = -13
+};
+
+/* What HParams + the system object determine (myriad/config.py:61-112, systems/base.py:11-36). */
+typedef struct MyrDesc {
+  int32_t system_id;
+  int32_t optimizer;
+  int32_t integration_method;
+  int32_t intervals;
+  int32_t controls_per_interval;
+  int32_t n_params;            /* 0 => the system's constructor defaults */
+  int32_t terminal_cost;
+  int32_t reserved;
+  double T;                    /* horizon; <= 0 => system default */
+  double params[MYR_MAX_PARAMS];
+} MyrDesc;
+
+typedef struct MyrSizes {
+  int32_t n, m;                /* state / control dimension */
+  int32_t nx_nodes, nu_nodes;  /* rows of results['x'] / results['u'] */
+  int32_t nvars, ncon;
+  int32_t nodes, stages;       /* node/stage structure used by the block kernels */
+  int32_t nw, nc;              /* variables per node block, constraint rows per stage */
+  int32_t stage_nodes;         /* node blocks per stage row in Jblk */
+  int32_t reserved;
+  int64_t jac_block_doubles;   /* per instance: stages * stage_nodes * nc * nw */
+  int64_t hess_block_doubles;  /* per instance: nodes * nw (nw + 1) / 2 (packed upper, row-major) */
+  int64_t ipm_workspace_doubles; /* per instance */
+} MyrSizes;
+
+/* Options of the interior-point solve; zero / negative fields take the defaults noted (IPOPT's). */
+typedef struct MyrIpmOpts {
+  int32_t max_iter;        /* hp.max_iter (myriad/config.py:70); default 1000 */
+  int32_t max_ls;          /* backtracking steps; default 40 */
+  int32_t acceptable_iter; /* default 15 */
+  int32_t reserved;
+  double tol;              /* default 1e-8 */
+  double acceptable_tol;   /* default 1e-6 */
+  double mu_init;          /* default 0.1 */
+} MyrIpmOpts;
+
+int myr_abi_version(void);
+const char* myr_last_error(void);
+
+/* Sizes implied by a descriptor.  Replaces what the optimizers' __init__ derive
+ * (shooting.py:26-31, trapezoidal.py:25-29, hermite_simpson.py:28-30). */
+int myr_problem_sizes(const MyrDesc* desc, MyrSizes* out);
+
+/* K1.  Fused evaluation of objective, objective gradient, defect constraints and their block Jacobian
+ * (and, if lam != NULL and Hblk != NULL, the block Hessian of f + lam.c) for B instances in one launch.
+ * Replaces the four jitted callbacks of myriad/nlp_solvers/__init__.py:31-42 (fun, jac = jax.grad,
+ * constraints fun, constraints jac = jax.jacrev); the dense ncon x nvars Jacobian is returned in compact
+ * block form: Jblk[b][stage][k][r][i] = d c_{stage,r} / d v_{node(stage,k), i}.
+ * Any of f, grad, c, Jblk, Hblk may be NULL. */
+int myr_eval(const MyrDesc* desc, int B, const double* z, const double* lam,
+             double* f, double* grad, double* c, double* Jblk, double* Hblk, void* stream);
+
+/* K2.  Batched block-structured KKT solve
+ *     [ H + diag(sigma) + delta_w I    J^T      ] [ dz   ]     [ rhs_z ]
+ *     [ J                            -delta_c I ] [ dlam ] = - [ rhs_c ]
+ * by node-block elimination, Schur complement and block cyclic reduction.  sigma[i] = +inf marks an
+ * eliminated (fixed) variable.  inertia_ok[b] = 1 iff the matrix has exactly ncon negative and no zero
+ * eigenvalues.  Replaces the linear solver inside IPOPT (MUMPS) for this problem class.
+ * ws: device workspace of at least B * ipm_workspace_doubles doubles. */
+int myr_kkt_solve(const MyrDesc* desc, int B, const double* Hblk, const double* Jblk, const double* sigma,
+                  const double* rhs_z, const double* rhs_c, double delta_w, double delta_c,
+                  double* dz, double* dlam, int32_t* inertia_ok, double* ws, size_t ws_doubles, void* stream);
+
+/* K3.  Whole batched primal-dual interior-point solve: replaces cyipopt.minimize_ipopt at
+ * myriad/nlp_solvers/__init__.py:56-58.  z0/lb/ub per instance as the optimizers build them
+ * (guess, bounds; lb == ub fixes a variable).  Outputs: z (solution['x']), lam (solution.info['mult_g']),
+ * obj (solution['fun']), status/iters, zL/zU bound multipliers, kkt_err (scaled optimality error at
+ * exit), con_inf (max |c|). */
+int myr_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B,
+                  const double* z0, const double* lb, const double* ub,
+                  double* z, double* lam, double* zL, double* zU,
+                  double* obj, double* kkt_err, double* con_inf, int32_t* status, int32_t* iters,
+                  double* ws, size_t ws_doubles, void* stream);
+
+/* Post-solve verification rollout of the TRUE system under controls u with hp.integration_method:
+ * replaces get_state_trajectory_and_cost (myriad/utils.py:258-298).  u: [B][nu_rows][m];
+ * x0: [B][n]; xs: [B][num_steps+1][n] (may be NULL); cost: [B]. */
+int myr_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double* u, const double* x0,
+                     double* xs, double* cost, void* stream);
+
+/* Host twins (debug / CI only; HOST pointers; single-threaded). */
+int myr_host_eval(const MyrDesc* desc, int B, const double* z, const double* lam,
+                  double* f, double* grad, double* c, double* Jblk, double* Hblk);
+int myr_host_kkt_solve(const MyrDesc* desc, int B, const double* Hblk, const double* Jblk, const double* sigma,
+                       const double* rhs_z, const double* rhs_c, double delta_w, double delta_c,
+                       double* dz, double* dlam, int32_t* inertia_ok, double* ws, size_t ws_doubles);
+int myr_host_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B,
+                       const double* z0, const double* lb, const double* ub,
+                       double* z, double* lam, double* zL, double* zU,
+                       double* obj, double* kkt_err, double* con_inf, int32_t* status, int32_t* iters,
+                       double* ws, size_t ws_doubles);
+int myr_host_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double* u, const double* x0,
+                          double* xs, double* cost);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYRIAD_B200_H */

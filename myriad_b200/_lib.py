@@ -1,0 +1,120 @@
+"""ctypes binding of libmyriad_b200.so (C ABI in include/myriad_b200.h).
+
+The library is built in-tree by ``myriad_b200.build`` (``__graft_entry__.build()``).  There is no
+fallback: if the shared object is missing, importing the product raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmyriad_b200.so")
+
+MAX_PARAMS = 16
+
+SYSTEM_IDS = {
+  "SIMPLECASE": 0, "CARTPOLE": 1, "VANDERPOL": 2, "CANCERTREATMENT": 3, "MOULDFUNGICIDE": 4, "BIOREACTOR": 5,
+  "SIMPLECASEWITHBOUNDS": 6, "GLUCOSE": 7, "HARVEST": 8, "TIMBERHARVEST": 9,
+}
+OPT_SHOOTING, OPT_TRAPEZOIDAL, OPT_HERMITE_SIMPSON = 0, 1, 2
+METHOD_IDS = {"EULER": 0, "HEUN": 1, "MIDPOINT": 2, "RK4": 3}
+
+STATUS_NAMES = {0: "solved", 1: "acceptable", -1: "max_iter", -2: "line_search_failed", -3: "inertia_correction_failed",
+                -13: "invalid_number"}
+
+
+class MyrDesc(C.Structure):
+  _fields_ = [("system_id", C.c_int32), ("optimizer", C.c_int32), ("integration_method", C.c_int32),
+              ("intervals", C.c_int32), ("controls_per_interval", C.c_int32), ("n_params", C.c_int32),
+              ("terminal_cost", C.c_int32), ("reserved", C.c_int32), ("T", C.c_double),
+              ("params", C.c_double * MAX_PARAMS)]
+
+
+class MyrSizes(C.Structure):
+  _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("nx_nodes", C.c_int32), ("nu_nodes", C.c_int32),
+              ("nvars", C.c_int32), ("ncon", C.c_int32), ("nodes", C.c_int32), ("stages", C.c_int32),
+              ("nw", C.c_int32), ("nc", C.c_int32), ("stage_nodes", C.c_int32), ("reserved", C.c_int32),
+              ("jac_block_doubles", C.c_int64), ("hess_block_doubles", C.c_int64),
+              ("ipm_workspace_doubles", C.c_int64)]
+
+
+class MyrIpmOpts(C.Structure):
+  _fields_ = [("max_iter", C.c_int32), ("max_ls", C.c_int32), ("acceptable_iter", C.c_int32), ("reserved", C.c_int32),
+              ("tol", C.c_double), ("acceptable_tol", C.c_double), ("mu_init", C.c_double)]
+
+
+class MyriadError(RuntimeError):
+  pass
+
+
+_P = C.c_void_p
+_lib = None
+
+EXPORTS = ["myr_abi_version", "myr_last_error", "myr_problem_sizes", "myr_eval", "myr_kkt_solve", "myr_ipm_solve",
+           "myr_rollout_cost", "myr_host_eval", "myr_host_kkt_solve", "myr_host_ipm_solve", "myr_host_rollout_cost"]
+
+
+def lib() -> C.CDLL:
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise MyriadError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(nvcc, sm_100a).  myriad_b200 has no CPU fallback.")
+  L = C.CDLL(LIB_PATH)
+  L.myr_abi_version.restype = C.c_int
+  L.myr_last_error.restype = C.c_char_p
+  L.myr_problem_sizes.argtypes = [C.POINTER(MyrDesc), C.POINTER(MyrSizes)]
+  ev = [C.POINTER(MyrDesc), C.c_int, _P, _P, _P, _P, _P, _P, _P]
+  L.myr_eval.argtypes = ev + [_P]
+  L.myr_host_eval.argtypes = ev
+  kk = [C.POINTER(MyrDesc), C.c_int, _P, _P, _P, _P, _P, C.c_double, C.c_double, _P, _P, _P, _P, C.c_size_t]
+  L.myr_kkt_solve.argtypes = kk + [_P]
+  L.myr_host_kkt_solve.argtypes = kk
+  ip = [C.POINTER(MyrDesc), C.POINTER(MyrIpmOpts), C.c_int] + [_P] * 12 + [_P, C.c_size_t]
+  L.myr_ipm_solve.argtypes = ip + [_P]
+  L.myr_host_ipm_solve.argtypes = ip
+  ro = [C.POINTER(MyrDesc), C.c_int, C.c_int, _P, _P, _P, _P]
+  L.myr_rollout_cost.argtypes = ro + [_P]
+  L.myr_host_rollout_cost.argtypes = ro
+  for name in EXPORTS:
+    if name not in ("myr_abi_version", "myr_last_error"):
+      getattr(L, name).restype = C.c_int
+  _lib = L
+  return L
+
+
+def check(rc: int) -> None:
+  if rc != 0:
+    msg = lib().myr_last_error().decode()
+    if rc == -1:
+      raise KeyError(msg)  # the reference raises KeyError / ValueError on unknown enums
+    if rc == -2:
+      raise NotImplementedError(msg)
+    raise MyriadError(f"myriad_b200 error {rc}: {msg}")
+
+
+def make_desc(system: str, optimizer: int, method: str, intervals: int, cpi: int = 1, T: float = 0.0, params=None,
+              terminal_cost: bool = False) -> MyrDesc:
+  d = MyrDesc()
+  if system not in SYSTEM_IDS:
+    raise KeyError(f"system {system} has no device implementation")
+  d.system_id = SYSTEM_IDS[system]
+  d.optimizer = int(optimizer)
+  d.integration_method = METHOD_IDS[method]
+  d.intervals = int(intervals)
+  d.controls_per_interval = int(cpi)
+  d.T = float(T)
+  d.terminal_cost = int(bool(terminal_cost))
+  if params:
+    d.n_params = len(params)
+    for i, v in enumerate(params):
+      d.params[i] = float(v)
+  return d
+
+
+def problem_sizes(desc: MyrDesc) -> MyrSizes:
+  s = MyrSizes()
+  check(lib().myr_problem_sizes(C.byref(desc), C.byref(s)))
+  return s

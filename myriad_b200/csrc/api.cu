@@ -1,0 +1,110 @@
+// C ABI (include/myriad_b200.h): error state and dispatch to the per-system tables (sys_unit.cu).
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/myriad_b200.h"
+#include "common.cuh"
+#include "kernels_decl.h"
+
+namespace myr {
+
+static thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, const char* a, long long v) {
+  snprintf(g_err, sizeof(g_err), fmt, a, v);
+  return code;
+}
+
+double system_default_T(int id) {
+  switch (id) {  // T of each system's constructor
+    case MYR_SYS_SIMPLECASE: return 1.0;
+    case MYR_SYS_CARTPOLE: return 2.0;
+    case MYR_SYS_VANDERPOL: return 10.0;
+    case MYR_SYS_CANCERTREATMENT: return 20.0;
+    case MYR_SYS_MOULDFUNGICIDE: return 5.0;
+    case MYR_SYS_BIOREACTOR: return 2.0;
+    case MYR_SYS_SIMPLECASEWITHBOUNDS: return 1.0;
+    case MYR_SYS_GLUCOSE: return 0.2;
+    case MYR_SYS_HARVEST: return 10.0;
+    case MYR_SYS_TIMBERHARVEST: return 5.0;
+    default: return 1.0;
+  }
+}
+
+}  // namespace myr
+
+using namespace myr;
+
+// Systems compiled into this build: MYR_BUILD_SYSTEMS(X) is passed by build.py, default = all generated.
+#ifndef MYR_BUILD_SYSTEMS
+#define MYR_BUILD_SYSTEMS(X) MYR_FOR_EACH_SYSTEM(X)
+#endif
+
+#define MYR_DECL(SYS) extern "C" const myr::SysVTable* myr_vtable_##SYS(void);
+MYR_BUILD_SYSTEMS(MYR_DECL)
+#undef MYR_DECL
+
+static const SysVTable* find_system(int id) {
+#define MYR_TRY(SYS) if (SYS::id == id) return myr_vtable_##SYS();
+  MYR_BUILD_SYSTEMS(MYR_TRY)
+#undef MYR_TRY
+  fail(MYR_E_BADARG, "unknown or not-built system_id %s%lld", "", id);
+  return nullptr;
+}
+
+#define MYR_GET(desc)                                                 \
+  if (!(desc)) return fail(MYR_E_BADARG, "null descriptor%s", "", 0); \
+  const SysVTable* vt = find_system((desc)->system_id);               \
+  if (!vt) return MYR_E_BADARG;
+
+extern "C" int myr_abi_version(void) { return MYR_ABI_VERSION; }
+extern "C" const char* myr_last_error(void) { return g_err; }
+
+extern "C" int myr_problem_sizes(const MyrDesc* desc, MyrSizes* out) {
+  if (!out) return fail(MYR_E_BADARG, "null output%s", "", 0);
+  memset(out, 0, sizeof(*out));
+  MYR_GET(desc);
+  return vt->sizes(desc, out);
+}
+extern "C" int myr_eval(const MyrDesc* desc, int B, const double* z, const double* lam, double* f, double* grad, double* c, double* Jblk,
+                        double* Hblk, void* stream) {
+  MYR_GET(desc);
+  return vt->eval(desc, B, z, lam, f, grad, c, Jblk, Hblk, stream);
+}
+extern "C" int myr_host_eval(const MyrDesc* desc, int B, const double* z, const double* lam, double* f, double* grad, double* c,
+                             double* Jblk, double* Hblk) {
+  MYR_GET(desc);
+  return vt->host_eval(desc, B, z, lam, f, grad, c, Jblk, Hblk);
+}
+extern "C" int myr_kkt_solve(const MyrDesc* desc, int B, const double* Hblk, const double* Jblk, const double* sigma, const double* rhs_z,
+                             const double* rhs_c, double delta_w, double delta_c, double* dz, double* dlam, int32_t* inertia_ok, double* ws,
+                             size_t ws_doubles, void* stream) {
+  MYR_GET(desc);
+  return vt->kkt(desc, B, Hblk, Jblk, sigma, rhs_z, rhs_c, delta_w, delta_c, dz, dlam, inertia_ok, ws, ws_doubles, stream);
+}
+extern "C" int myr_host_kkt_solve(const MyrDesc* desc, int B, const double* Hblk, const double* Jblk, const double* sigma,
+                                  const double* rhs_z, const double* rhs_c, double delta_w, double delta_c, double* dz, double* dlam,
+                                  int32_t* inertia_ok, double* ws, size_t ws_doubles) {
+  MYR_GET(desc);
+  return vt->host_kkt(desc, B, Hblk, Jblk, sigma, rhs_z, rhs_c, delta_w, delta_c, dz, dlam, inertia_ok, ws, ws_doubles);
+}
+extern "C" int myr_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const double* z0, const double* lb, const double* ub, double* z,
+                             double* lam, double* zL, double* zU, double* obj, double* kkt_err, double* con_inf, int32_t* status, int32_t* iters,
+                             double* ws, size_t ws_doubles, void* stream) {
+  MYR_GET(desc);
+  return vt->ipm(desc, opts, B, z0, lb, ub, z, lam, zL, zU, obj, kkt_err, con_inf, status, iters, ws, ws_doubles, stream);
+}
+extern "C" int myr_host_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const double* z0, const double* lb, const double* ub,
+                                  double* z, double* lam, double* zL, double* zU, double* obj, double* kkt_err, double* con_inf,
+                                  int32_t* status, int32_t* iters, double* ws, size_t ws_doubles) {
+  MYR_GET(desc);
+  return vt->host_ipm(desc, opts, B, z0, lb, ub, z, lam, zL, zU, obj, kkt_err, con_inf, status, iters, ws, ws_doubles);
+}
+extern "C" int myr_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double* u, const double* x0, double* xs, double* cost,
+                                void* stream) {
+  MYR_GET(desc);
+  return vt->rollout(desc, B, nu_rows, u, x0, xs, cost, stream);
+}
+extern "C" int myr_host_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double* u, const double* x0, double* xs, double* cost) {
+  MYR_GET(desc);
+  return vt->host_rollout(desc, B, nu_rows, u, x0, xs, cost);
+}

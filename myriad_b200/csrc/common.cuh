@@ -1,0 +1,210 @@
+// Common device helpers: problem descriptor, block reductions, small symmetric-indefinite
+// factorisation with inertia (Bunch-Parlett complete pivoting) used by the KKT kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#pragma nv_diag_suppress 177   // generated system code declares symbols it may not use
+#pragma nv_diag_suppress 550
+
+#include "systems_gen.cuh"
+
+namespace myr {
+
+constexpr int kMaxParams = 16;
+
+enum Method : int { EULER = 0, HEUN = 1, MIDPOINT = 2, RK4 = 3 };
+enum Optimizer : int { OPT_SHOOTING = 0, OPT_TRAPEZOIDAL = 1, OPT_HERMITE_SIMPSON = 2 };
+
+// Kernel-side problem description (by value in kernel params -> constant bank).
+struct Problem {
+  int B;          // instances
+  int N;          // collocation intervals, or shooting intervals K
+  int cpi;        // controls per interval (shooting)
+  int method;     // Method
+  int nvars;      // reference decision-vector length
+  int ncon;       // reference constraint-vector length
+  int terminal_cost;
+  double T;
+  double h;       // T / N (collocation) or T / (N * cpi) (shooting step)
+  double p[kMaxParams];
+};
+
+__host__ __device__ __forceinline__ constexpr int packed_size(int n) { return n * (n + 1) / 2; }
+// packed upper triangle, row-major
+__host__ __device__ __forceinline__ int pidx(int i, int j, int n) {
+  if (i > j) { int t = i; i = j; j = t; }
+  return i * n - (i * (i - 1)) / 2 + (j - i);
+}
+
+// ------------------------------------------------------------------ execution model
+// Every per-instance routine is written once and compiled twice: for the device (one CTA per
+// instance, MYR_NT threads striding over nodes/stages, __syncthreads between phases) and for the
+// host (one "thread", barriers vanish).  The host build is a debugging twin used by CPU tests; the
+// product path never dispatches to it.
+#ifdef __CUDA_ARCH__
+#define MYR_TID (int(threadIdx.x))
+#define MYR_NT (int(blockDim.x))
+#define MYR_SYNC() __syncthreads()
+#else
+#define MYR_TID 0
+#define MYR_NT 1
+#define MYR_SYNC() ((void)0)
+#endif
+#define MYR_HDI __host__ __device__ __forceinline__
+#define MYR_HDN __host__ __device__ __noinline__
+
+// ------------------------------------------------------------------ block reductions
+// red: shared scratch of >= 33 doubles.  All threads of the CTA must call.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <int OP>  // 0 sum, 1 max, 2 min
+__host__ __device__ __forceinline__ double block_reduce(double v, double* red) {
+#ifndef __CUDA_ARCH__
+  (void)red;
+  return v;
+#else
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = OP == 0 ? warp_sum(v) : (OP == 1 ? warp_max(v) : warp_min(v));
+  __syncthreads();  // protect red from a previous use
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double r = OP == 0 ? 0.0 : (OP == 1 ? -INFINITY : INFINITY);
+  if (lane < nw) r = red[lane];
+  r = OP == 0 ? warp_sum(r) : (OP == 1 ? warp_max(r) : warp_min(r));
+  return r;  // every thread has the result
+#endif
+}
+MYR_HDI double block_sum(double v, double* red) { return block_reduce<0>(v, red); }
+MYR_HDI double block_max(double v, double* red) { return block_reduce<1>(v, red); }
+MYR_HDI double block_min(double v, double* red) { return block_reduce<2>(v, red); }
+
+// NaN-propagating max for error norms: fmax() drops NaNs, which would hide a blown-up lane.
+MYR_HDI double nanmax(double a, double b) { return (a != a || b != b) ? NAN : fmax(a, b); }
+
+// ------------------------------------------------------------------ small symmetric indefinite inverse + inertia
+// A: full symmetric N x N (row-major, both triangles valid) is destroyed.  inv: full N x N out.
+// mask bit i set => variable i is eliminated (fixed): it is skipped, its row/col of inv are zero and it
+// does not count in the inertia.  Bunch-Parlett: complete pivoting with 1x1 / 2x2 pivots.
+template <int N>
+__host__ __device__ inline void sym_inverse_inertia(double* A, uint32_t mask, double* inv, int& npos, int& nneg, int& nzero) {
+  int perm[N];   // perm[k] = original index placed at position k (active ones first)
+  int na = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) if (!((mask >> i) & 1u)) perm[na++] = i;
+  for (int i = 0, k = na; i < N; ++i) if ((mask >> i) & 1u) perm[k++] = i;
+  // work on permuted copy M (na x na) held in local array
+  double M[N * N];
+  double scale = 0.0;
+  for (int i = 0; i < na; ++i)
+    for (int j = 0; j < na; ++j) { M[i * N + j] = A[perm[i] * N + perm[j]]; scale = fmax(scale, fabs(M[i * N + j])); }
+  int p2[N];       // second-level permutation from pivoting (positions within active set)
+  for (int i = 0; i < na; ++i) p2[i] = i;
+  int piv2[N];     // piv2[k] = 1 if a 2x2 pivot starts at k
+  double L[N * N]; // unit lower factors (column k / k,k+1)
+  for (int i = 0; i < N * N; ++i) L[i] = 0.0;
+  for (int i = 0; i < N; ++i) piv2[i] = 0;
+  const double alpha = 0.6403882032022076;
+  const double tiny = 1e-13 * fmax(scale, 1e-300);
+  npos = nneg = nzero = 0;
+  int k = 0;
+  while (k < na) {
+    // largest diagonal and largest off-diagonal in trailing block
+    double mu0 = -1.0, mu1 = -1.0; int r = k, pp = k, qq = k;
+    for (int i = k; i < na; ++i) {
+      double d = fabs(M[i * N + i]);
+      if (d > mu0) { mu0 = d; r = i; }
+      for (int j = k; j < i; ++j) { double o = fabs(M[i * N + j]); if (o > mu1) { mu1 = o; pp = i; qq = j; } }
+    }
+    auto swap_sym = [&](int a, int b) {
+      if (a == b) return;
+      for (int j = 0; j < na; ++j) { double t = M[a * N + j]; M[a * N + j] = M[b * N + j]; M[b * N + j] = t; }
+      for (int i = 0; i < na; ++i) { double t = M[i * N + a]; M[i * N + a] = M[i * N + b]; M[i * N + b] = t; }
+      for (int j = 0; j < k; ++j) { double t = L[a * N + j]; L[a * N + j] = L[b * N + j]; L[b * N + j] = t; }
+      int t = p2[a]; p2[a] = p2[b]; p2[b] = t;
+    };
+    if (mu0 <= tiny && mu1 <= tiny) {  // remaining block is numerically zero
+      nzero += na - k;
+      for (int i = k; i < na; ++i) { M[i * N + i] = 1.0; for (int j = k; j < na; ++j) if (j != i) M[i * N + j] = 0.0; }
+      break;
+    }
+    if (mu0 >= alpha * mu1) {
+      swap_sym(k, r);
+      const double d = M[k * N + k];
+      if (d > 0) ++npos; else ++nneg;
+      for (int i = k + 1; i < na; ++i) L[i * N + k] = M[i * N + k] / d;
+      for (int i = k + 1; i < na; ++i)
+        for (int j = k + 1; j <= i; ++j) {
+          M[i * N + j] -= L[i * N + k] * d * L[j * N + k];
+          M[j * N + i] = M[i * N + j];
+        }
+      k += 1;
+    } else {
+      // 2x2 pivot on (qq, pp), qq < pp
+      swap_sym(k, qq);
+      swap_sym(k + 1, pp);
+      const double a = M[k * N + k], b = M[(k + 1) * N + k], c = M[(k + 1) * N + k + 1];
+      const double det = a * c - b * b;  // < 0 by the pivot test
+      ++npos; ++nneg;
+      piv2[k] = 1;
+      for (int i = k + 2; i < na; ++i) {
+        const double s0 = M[i * N + k], s1 = M[i * N + k + 1];
+        L[i * N + k] = (s0 * c - s1 * b) / det;
+        L[i * N + k + 1] = (-s0 * b + s1 * a) / det;
+      }
+      for (int i = k + 2; i < na; ++i)
+        for (int j = k + 2; j <= i; ++j) {
+          const double s0 = M[j * N + k], s1 = M[j * N + k + 1];
+          M[i * N + j] -= L[i * N + k] * s0 + L[i * N + k + 1] * s1;
+          M[j * N + i] = M[i * N + j];
+        }
+      k += 2;
+    }
+  }
+  // M now holds D on its (block) diagonal.  Build inverse column by column.
+  for (int i = 0; i < N * N; ++i) inv[i] = 0.0;
+  for (int col = 0; col < na; ++col) {
+    double y[N];
+    for (int i = 0; i < na; ++i) y[i] = (p2[i] == col) ? 1.0 : 0.0;   // P^T e_col
+    for (int i = 0; i < na; ++i) {                                  // L y = b
+      double s = y[i];
+      for (int j = 0; j < i; ++j) s -= L[i * N + j] * y[j];
+      y[i] = s;
+    }
+    for (int i = 0; i < na; ++i) {                                  // D^-1
+      if (piv2[i]) {
+        const double a = M[i * N + i], b = M[(i + 1) * N + i], c = M[(i + 1) * N + i + 1];
+        const double det = a * c - b * b;
+        const double y0 = y[i], y1 = y[i + 1];
+        y[i] = (c * y0 - b * y1) / det;
+        y[i + 1] = (-b * y0 + a * y1) / det;
+        ++i;
+      } else {
+        y[i] /= M[i * N + i];
+      }
+    }
+    for (int i = na - 1; i >= 0; --i) {                             // L^T x = y
+      double s = y[i];
+      for (int j = i + 1; j < na; ++j) s -= L[j * N + i] * y[j];
+      y[i] = s;
+    }
+    for (int i = 0; i < na; ++i) inv[perm[p2[i]] * N + perm[col]] = y[i];
+  }
+}
+
+}  // namespace myr

@@ -1,0 +1,433 @@
+// Kernel templates and per-system launchers.  Compiled once per system (sys_unit.cu) so the build
+// parallelises; api.cu dispatches through the per-system tables.
+#pragma once
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/myriad_b200.h"
+#include "engine.cuh"
+#include "rollout.cuh"
+#include "kernels_decl.h"
+
+namespace myr {
+
+int fail(int code, const char* fmt, const char* a = "", long long v = 0);  // api.cu
+double system_default_T(int id);                                            // api.cu
+
+template <class Sys>
+static int make_problem(const MyrDesc* d, int B, Problem& P) {
+  memset(&P, 0, sizeof(P));
+  if (!d) return fail(MYR_E_BADARG, "null descriptor%s", "");
+  if (d->intervals < 1) return fail(MYR_E_BADARG, "intervals must be >= 1 (got %s%lld)", "", d->intervals);
+  if (B < 0) return fail(MYR_E_BADARG, "negative batch%s", "");
+  P.B = B;
+  P.N = d->intervals;
+  P.cpi = d->optimizer == MYR_OPT_SHOOTING ? d->controls_per_interval : 1;
+  if (P.cpi < 1) return fail(MYR_E_BADARG, "controls_per_interval must be >= 1%s", "");
+  P.method = d->integration_method;
+  if (P.method < 0 || P.method > 3) return fail(MYR_E_BADARG, "unknown integration_method %s%lld", "", P.method);
+  P.terminal_cost = d->terminal_cost;
+  P.T = d->T > 0 ? d->T : system_default_T(Sys::id);
+  Sys::default_params(P.p);
+  if (d->n_params > 0) {
+    if (d->n_params != Sys::np) return fail(MYR_E_BADARG, "n_params does not match system %s (%lld given)", Sys::name, d->n_params);
+    for (int i = 0; i < Sys::np; ++i) P.p[i] = d->params[i];
+  }
+  return MYR_OK;
+}
+
+template <class Sys, class F>
+static int dispatch_scheme(const MyrDesc* d, int B, F&& fn) {
+  Problem P;
+  int rc = make_problem<Sys>(d, B, P);
+  if (rc) return rc;
+  switch (d->optimizer) {
+    case MYR_OPT_TRAPEZOIDAL: {
+      using S = Trapezoid<Sys>;
+      P.h = P.T / P.N; P.nvars = S::nvars(P); P.ncon = S::ncon(P);
+      return fn(S{}, P);
+    }
+    case MYR_OPT_HERMITE_SIMPSON: {
+      using S = HermiteSimpson<Sys>;
+      P.h = P.T / P.N; P.nvars = S::nvars(P); P.ncon = S::ncon(P);
+      return fn(S{}, P);
+    }
+    case MYR_OPT_SHOOTING:
+      return fail(MYR_E_UNSUPPORTED, "SHOOTING block kernels are not built yet for %s", Sys::name);
+    default:
+      return fail(MYR_E_BADARG, "unknown optimizer %s%lld", "", d->optimizer);
+  }
+}
+
+
+static int cuda_check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MYR_E_CUDA, "%s: CUDA error", (std::string(what) + ": " + cudaGetErrorString(e)).c_str());
+  return MYR_OK;
+}
+
+static int threads_for(int Q) {
+  int t = (Q + 31) / 32 * 32;
+  if (t < 32) t = 32;
+  if (t > 256) t = 256;
+  return t;
+}
+
+template <class Sys>
+int sys_problem_sizes(const MyrDesc* desc, MyrSizes* out) {
+  if (desc->optimizer == MYR_OPT_SHOOTING) {
+    Problem P;
+    int rc = make_problem<Sys>(desc, 0, P);
+    if (rc) return rc;
+    const int mc = P.method == RK4 ? 2 : 1;
+    out->n = Sys::n; out->m = Sys::m;
+    out->nx_nodes = P.N + 1; out->nu_nodes = mc * P.N * P.cpi + 1;
+    out->nvars = out->nx_nodes * Sys::n + out->nu_nodes * Sys::m;
+    out->ncon = P.N * Sys::n;
+    return (int)MYR_OK;
+  }
+  return dispatch_scheme<Sys>(desc, 0, [&](auto s, const Problem& P) {
+    using S = decltype(s);
+    const Layout<S> L(P);
+    out->n = S::n; out->m = S::m;
+    out->nx_nodes = out->nu_nodes = L.Q;
+    out->nvars = P.nvars; out->ncon = P.ncon;
+    out->nodes = L.Q; out->stages = L.St; out->nw = S::NW; out->nc = S::NC;
+    out->stage_nodes = S::kMaxStageNodes;
+    out->jac_block_doubles = (int64_t)L.St * S::kMaxStageNodes * S::NC * S::NW;
+    out->hess_block_doubles = (int64_t)L.Q * S::NWP;
+    out->ipm_workspace_doubles = L.total;
+    return (int)MYR_OK;
+  });
+}
+
+// ------------------------------------------------------------------ K1 kernel
+// One CTA per instance, one thread per node.  phi/psi meet in shared memory to form the stage constraints;
+// each node writes its Jacobian blocks straight into the compact stage-row layout.
+template <class S, bool kHost>
+__host__ __device__ inline void eval_instance(const Problem& P, int b, const double* z_all, const double* lam_all, double* f_out,
+                                              double* grad_out, double* c_out, double* J_out, double* H_out,
+                                              double* sphi, double* spsi, double* red) {
+  const Layout<S> L(P);
+  const double* z = z_all + (long long)b * P.nvars;
+  const double* lam = lam_all ? lam_all + (long long)b * P.ncon : nullptr;
+  const bool want_h = lam && H_out;
+  const long long jstride = (long long)L.St * S::kMaxStageNodes * S::NC * S::NW;
+  double fsum = 0.0;
+  for (int q = MYR_TID; q < L.Q; q += MYR_NT) {
+    double v[S::NW], lp[S::NC], ls[S::NC];
+#pragma unroll
+    for (int i = 0; i < S::NW; ++i) v[i] = z[S::zidx(P, q, i)];
+    const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
+#pragma unroll
+    for (int r = 0; r < S::NC; ++r) {
+      lp[r] = (want_h && jp >= 0) ? lam[S::cidx(P, jp, r)] : 0.0;
+      ls[r] = (want_h && js >= 0) ? lam[S::cidx(P, js, r)] : 0.0;
+    }
+    double ell, gl[S::NW], phi[S::NC], psi[S::NC], G[S::NC * S::NW], F[S::NC * S::NW], W[S::NWP];
+    if (want_h) S::template eval_node<2>(P, q, v, lp, ls, ell, gl, phi, psi, G, F, W);
+    else S::template eval_node<1>(P, q, v, lp, ls, ell, gl, phi, psi, G, F, W);
+    fsum += ell;
+#pragma unroll
+    for (int r = 0; r < S::NC; ++r) { sphi[q * S::NC + r] = phi[r]; spsi[q * S::NC + r] = psi[r]; }
+    if (grad_out) {
+#pragma unroll
+      for (int i = 0; i < S::NW; ++i) grad_out[(long long)b * P.nvars + S::zidx(P, q, i)] = gl[i];
+    }
+    if (J_out) {
+      double* Jb = J_out + (long long)b * jstride;
+      if (jp >= 0) {
+        double* dst = Jb + ((long long)jp * S::kMaxStageNodes + S::phi_slot(P, q)) * S::NC * S::NW;
+#pragma unroll
+        for (int i = 0; i < S::NC * S::NW; ++i) dst[i] = G[i];
+      }
+      if (js >= 0) {
+        double* dst = Jb + ((long long)js * S::kMaxStageNodes + S::psi_slot(P, q)) * S::NC * S::NW;
+#pragma unroll
+        for (int i = 0; i < S::NC * S::NW; ++i) dst[i] = F[i];
+      }
+    }
+    if (want_h) {
+      double* dst = H_out + ((long long)b * L.Q + q) * S::NWP;
+#pragma unroll
+      for (int i = 0; i < S::NWP; ++i) dst[i] = W[i];
+    }
+  }
+  const double f = block_sum(fsum, red);
+  MYR_SYNC();
+  if (f_out && MYR_TID == 0) f_out[b] = f;
+  if (c_out) {
+    for (int j = MYR_TID; j < L.St; j += MYR_NT) {
+      const int nk = S::stage_nodes(P, j);
+#pragma unroll
+      for (int r = 0; r < S::NC; ++r) {
+        double a = 0.0;
+        for (int k = 0; k < nk; ++k) {
+          int role; const int q = S::stage_node(P, j, k, role);
+          a += role ? spsi[q * S::NC + r] : sphi[q * S::NC + r];
+        }
+        c_out[(long long)b * P.ncon + S::cidx(P, j, r)] = a;
+      }
+    }
+  }
+}
+
+template <class S>
+__global__ void __launch_bounds__(256) eval_kernel(Problem P, const double* z, const double* lam, double* f, double* grad, double* c,
+                                                   double* Jblk, double* Hblk) {
+  extern __shared__ double smem[];
+  const int Q = S::num_nodes(P);
+  double* red = smem;
+  double* sphi = smem + 64;
+  double* spsi = sphi + Q * S::NC;
+  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+    eval_instance<S, false>(P, b, z, lam, f, grad, c, Jblk, Hblk, sphi, spsi, red);
+    __syncthreads();
+  }
+}
+
+template <class Sys>
+int sys_eval(const MyrDesc* desc, int B, const double* z, const double* lam, double* f, double* grad, double* c,
+                        double* Jblk, double* Hblk, void* stream) {
+  return dispatch_scheme<Sys>(desc, B, [&](auto s, const Problem& P) {
+    using S = decltype(s);
+    if (B == 0) return (int)MYR_OK;
+    if (!z) return fail(MYR_E_BADARG, "z is null%s", "");
+    const int Q = S::num_nodes(P);
+    const size_t sm = (64 + 2 * (size_t)Q * S::NC) * sizeof(double);
+    if (sm > 48 * 1024) cudaFuncSetAttribute(eval_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    eval_kernel<S><<<B, threads_for(Q), sm, (cudaStream_t)stream>>>(P, z, lam, f, grad, c, Jblk, Hblk);
+    return cuda_check("myr_eval");
+  });
+}
+
+template <class Sys>
+int sys_host_eval(const MyrDesc* desc, int B, const double* z, const double* lam, double* f, double* grad, double* c,
+                             double* Jblk, double* Hblk) {
+  return dispatch_scheme<Sys>(desc, B, [&](auto s, const Problem& P) {
+    using S = decltype(s);
+    const int Q = S::num_nodes(P);
+    std::vector<double> sh(64 + 2 * (size_t)Q * S::NC);
+    for (int b = 0; b < B; ++b)
+      eval_instance<S, true>(P, b, z, lam, f, grad, c, Jblk, Hblk, sh.data() + 64, sh.data() + 64 + Q * S::NC, sh.data());
+    return (int)MYR_OK;
+  });
+}
+
+// ------------------------------------------------------------------ K2 kernel
+template <class S>
+__host__ __device__ inline void kkt_instance(const Problem& P, int b, const double* Hblk, const double* Jblk, const double* sigma,
+                                             const double* rhs_z, const double* rhs_c, double dw, double dc, double* dz, double* dlam,
+                                             int32_t* inertia_ok, double* work, long long stride, double* cr, double* red,
+                                             double* sig_sh, uint32_t* fix_sh) {
+  const Layout<S> L(P);
+  double* w = work + (long long)b * stride;
+  const long long jstride = (long long)L.St * S::kMaxStageNodes * S::NC * S::NW;
+  const double* Jb = Jblk + (long long)b * jstride;
+  for (int q = MYR_TID; q < L.Q; q += MYR_NT) {
+    const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
+    for (int i = 0; i < S::NC * S::NW; ++i) {
+      w[L.G + q * S::NC * S::NW + i] = jp >= 0 ? Jb[((long long)jp * S::kMaxStageNodes + S::phi_slot(P, q)) * S::NC * S::NW + i] : 0.0;
+      w[L.F + q * S::NC * S::NW + i] = js >= 0 ? Jb[((long long)js * S::kMaxStageNodes + S::psi_slot(P, q)) * S::NC * S::NW + i] : 0.0;
+    }
+    for (int i = 0; i < S::NWP; ++i) w[L.W + q * S::NWP + i] = Hblk[((long long)b * L.Q + q) * S::NWP + i];
+    uint32_t fm = 0;
+    for (int i = 0; i < S::NW; ++i) {
+      const int id = S::zidx(P, q, i);
+      const double sg = sigma[(long long)b * P.nvars + id];
+      const bool fx = isinf(sg);
+      if (fx) fm |= 1u << i;
+      sig_sh[q * S::NW + i] = fx ? 0.0 : sg;
+      w[L.rb + q * S::NW + i] = fx ? 0.0 : rhs_z[(long long)b * P.nvars + id];
+    }
+    fix_sh[q] = fm;
+  }
+  for (int j = MYR_TID; j < L.St; j += MYR_NT)
+    for (int r = 0; r < S::NC; ++r) w[L.c + j * S::NC + r] = rhs_c[(long long)b * P.ncon + S::cidx(P, j, r)];
+  MYR_SYNC();
+  const bool ok = kkt_solve<S>(P, L, w, sig_sh, fix_sh, dw, dc, cr, red);
+  for (int q = MYR_TID; q < L.Q; q += MYR_NT)
+    for (int i = 0; i < S::NW; ++i) dz[(long long)b * P.nvars + S::zidx(P, q, i)] = w[L.dz + q * S::NW + i];
+  for (int j = MYR_TID; j < L.St; j += MYR_NT)
+    for (int r = 0; r < S::NC; ++r) dlam[(long long)b * P.ncon + S::cidx(P, j, r)] = w[L.dlam + j * S::NC + r];
+  if (MYR_TID == 0 && inertia_ok) inertia_ok[b] = ok ? 1 : 0;
+}
+
+// shared-memory carve-up shared by the KKT and IPM kernels
+template <class S>
+struct SmemPlan {
+  size_t red, sig, fix, cr, total;
+  bool cr_in_smem;
+  explicit SmemPlan(const Problem& P, size_t budget = 200 * 1024) {
+    const Layout<S> L(P);
+    red = 64 * sizeof(double);
+    sig = (size_t)L.Q * S::NW * sizeof(double);
+    fix = (((size_t)L.Q * sizeof(uint32_t)) + 15) & ~(size_t)15;
+    cr = (size_t)L.cr_doubles() * sizeof(double);
+    cr_in_smem = red + sig + fix + cr <= budget;
+    total = red + sig + fix + (cr_in_smem ? cr : 0);
+  }
+};
+
+template <class S>
+__global__ void __launch_bounds__(256) kkt_kernel(Problem P, const double* Hblk, const double* Jblk, const double* sigma, const double* rhs_z,
+                                                  const double* rhs_c, double dw, double dc, double* dz, double* dlam, int32_t* inertia_ok,
+                                                  double* work, long long stride, int cr_in_smem) {
+  extern __shared__ double smem[];
+  const Layout<S> L(P);
+  double* red = smem;
+  double* sig = red + 64;
+  uint32_t* fix = reinterpret_cast<uint32_t*>(sig + L.Q * S::NW);
+  double* crs = reinterpret_cast<double*>(reinterpret_cast<char*>(fix) + ((((size_t)L.Q * sizeof(uint32_t)) + 15) & ~(size_t)15));
+  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+    double* cr = cr_in_smem ? crs : work + (long long)b * stride + L.crD;
+    kkt_instance<S>(P, b, Hblk, Jblk, sigma, rhs_z, rhs_c, dw, dc, dz, dlam, inertia_ok, work, stride, cr, red, sig, fix);
+    __syncthreads();
+  }
+}
+
+template <class Sys>
+int sys_kkt_solve(const MyrDesc* desc, int B, const double* Hblk, const double* Jblk, const double* sigma, const double* rhs_z,
+                             const double* rhs_c, double delta_w, double delta_c, double* dz, double* dlam, int32_t* inertia_ok, double* ws,
+                             size_t ws_doubles, void* stream) {
+  return dispatch_scheme<Sys>(desc, B, [&](auto s, const Problem& P) {
+    using S = decltype(s);
+    if (B == 0) return (int)MYR_OK;
+    const Layout<S> L(P);
+    if (ws_doubles < (size_t)B * L.total) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)B * L.total);
+    const SmemPlan<S> sp(P);
+    if (sp.total > 48 * 1024) cudaFuncSetAttribute(kkt_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+    kkt_kernel<S><<<B, threads_for(L.Q), sp.total, (cudaStream_t)stream>>>(P, Hblk, Jblk, sigma, rhs_z, rhs_c, delta_w, delta_c, dz, dlam,
+                                                                            inertia_ok, ws, L.total, sp.cr_in_smem ? 1 : 0);
+    return cuda_check("myr_kkt_solve");
+  });
+}
+
+template <class Sys>
+int sys_host_kkt_solve(const MyrDesc* desc, int B, const double* Hblk, const double* Jblk, const double* sigma,
+                                  const double* rhs_z, const double* rhs_c, double delta_w, double delta_c, double* dz, double* dlam,
+                                  int32_t* inertia_ok, double* ws, size_t ws_doubles) {
+  return dispatch_scheme<Sys>(desc, B, [&](auto s, const Problem& P) {
+    using S = decltype(s);
+    const Layout<S> L(P);
+    if (ws_doubles < (size_t)B * L.total) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)B * L.total);
+    std::vector<double> red(64), sig((size_t)L.Q * S::NW);
+    std::vector<uint32_t> fix(L.Q);
+    for (int b = 0; b < B; ++b)
+      kkt_instance<S>(P, b, Hblk, Jblk, sigma, rhs_z, rhs_c, delta_w, delta_c, dz, dlam, inertia_ok, ws, L.total, ws + (long long)b * L.total + L.crD,
+                      red.data(), sig.data(), fix.data());
+    return (int)MYR_OK;
+  });
+}
+
+// ------------------------------------------------------------------ K3 kernel
+inline IpmOpts make_opts(const MyrIpmOpts* o) {
+  IpmOpts r;
+  memset(&r, 0, sizeof(r));
+  r.max_iter = (o && o->max_iter > 0) ? o->max_iter : 1000;
+  r.max_ls = (o && o->max_ls > 0) ? o->max_ls : 40;
+  r.acceptable_iter = (o && o->acceptable_iter > 0) ? o->acceptable_iter : 15;
+  r.tol = (o && o->tol > 0) ? o->tol : 1e-8;
+  r.acceptable_tol = (o && o->acceptable_tol > 0) ? o->acceptable_tol : 1e-6;
+  r.mu_init = (o && o->mu_init > 0) ? o->mu_init : 0.1;
+  r.mu_min = 1e-11; r.kappa_eps = 10.0; r.kappa_mu = 0.2; r.theta_mu = 1.5; r.tau_min = 0.99;
+  r.bound_push = 1e-2; r.bound_frac = 1e-2; r.bound_relax = 1e-8; r.kappa_sigma = 1e10; r.s_max = 100.0;
+  r.delta_min = 1e-20; r.delta_0 = 1e-4; r.delta_max = 1e40; r.delta_c = 0.0;
+  r.kappa_w_minus = 1.0 / 3.0; r.kappa_w_plus = 8.0; r.kappa_w_plus_first = 100.0;
+  r.eta = 1e-4; r.rho = 0.1;
+  return r;
+}
+
+template <class S>
+__global__ void __launch_bounds__(256) ipm_kernel(Problem P, IpmOpts O, IpmIO io, int cr_in_smem) {
+  extern __shared__ double smem[];
+  const Layout<S> L(P);
+  double* red = smem;
+  double* sig = red + 64;
+  uint32_t* fix = reinterpret_cast<uint32_t*>(sig + L.Q * S::NW);
+  double* crs = reinterpret_cast<double*>(reinterpret_cast<char*>(fix) + ((((size_t)L.Q * sizeof(uint32_t)) + 15) & ~(size_t)15));
+  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+    double* cr = cr_in_smem ? crs : io.work + (long long)b * io.work_stride + L.crD;
+    ipm_solve_instance<S>(P, O, io, b, cr, red, sig, fix);
+    __syncthreads();
+  }
+}
+
+template <class Sys>
+int sys_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const double* z0, const double* lb, const double* ub, double* z,
+                             double* lam, double* zL, double* zU, double* obj, double* kkt_err, double* con_inf, int32_t* status, int32_t* iters,
+                             double* ws, size_t ws_doubles, void* stream) {
+  return dispatch_scheme<Sys>(desc, B, [&](auto s, const Problem& P) {
+    using S = decltype(s);
+    if (B == 0) return (int)MYR_OK;
+    if (!z0 || !lb || !ub || !z || !lam || !zL || !zU || !obj || !kkt_err || !con_inf || !status || !iters || !ws)
+      return fail(MYR_E_BADARG, "null buffer passed to myr_ipm_solve%s", "");
+    const Layout<S> L(P);
+    if (ws_doubles < (size_t)B * L.total) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)B * L.total);
+    IpmIO io{z0, lb, ub, z, lam, zL, zU, obj, kkt_err, con_inf, status, iters, ws, (long long)L.total};
+    const IpmOpts O = make_opts(opts);
+    const SmemPlan<S> sp(P);
+    if (sp.total > 48 * 1024) cudaFuncSetAttribute(ipm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+    ipm_kernel<S><<<B, threads_for(L.Q), sp.total, (cudaStream_t)stream>>>(P, O, io, sp.cr_in_smem ? 1 : 0);
+    return cuda_check("myr_ipm_solve");
+  });
+}
+
+template <class Sys>
+int sys_host_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const double* z0, const double* lb, const double* ub,
+                                  double* z, double* lam, double* zL, double* zU, double* obj, double* kkt_err, double* con_inf,
+                                  int32_t* status, int32_t* iters, double* ws, size_t ws_doubles) {
+  return dispatch_scheme<Sys>(desc, B, [&](auto s, const Problem& P) {
+    using S = decltype(s);
+    const Layout<S> L(P);
+    if (ws_doubles < (size_t)B * L.total) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)B * L.total);
+    IpmIO io{z0, lb, ub, z, lam, zL, zU, obj, kkt_err, con_inf, status, iters, ws, (long long)L.total};
+    const IpmOpts O = make_opts(opts);
+    std::vector<double> red(64), sig((size_t)L.Q * S::NW);
+    std::vector<uint32_t> fix(L.Q);
+    for (int b = 0; b < B; ++b)
+      ipm_solve_instance<S>(P, O, io, b, ws + (long long)b * L.total + L.crD, red.data(), sig.data(), fix.data());
+    return (int)MYR_OK;
+  });
+}
+
+// ------------------------------------------------------------------ verification rollout (utils.py:258-298)
+template <class Sys>
+__global__ void rollout_kernel(RolloutArgs A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < A.B) rollout_instance<Sys>(A, b);
+}
+
+template <class Sys>
+int sys_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double* u, const double* x0, double* xs, double* cost,
+                     void* stream) {
+  Problem P;
+  int rc = make_problem<Sys>(desc, B, P);
+  if (rc) return rc;
+  if (B == 0) return (int)MYR_OK;
+  RolloutArgs A = make_rollout_args<Sys>(P, desc->intervals * P.cpi, nu_rows, u, x0, xs, cost);
+  rollout_kernel<Sys><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A);
+  return cuda_check("myr_rollout_cost");
+}
+
+template <class Sys>
+int sys_host_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double* u, const double* x0, double* xs, double* cost) {
+  Problem P;
+  int rc = make_problem<Sys>(desc, B, P);
+  if (rc) return rc;
+  RolloutArgs A = make_rollout_args<Sys>(P, desc->intervals * P.cpi, nu_rows, u, x0, xs, cost);
+  for (int b = 0; b < B; ++b) rollout_instance<Sys>(A, b);
+  return (int)MYR_OK;
+}
+
+template <class Sys>
+SysVTable make_vtable() {
+  return SysVTable{Sys::id, Sys::name, &sys_problem_sizes<Sys>, &sys_eval<Sys>, &sys_host_eval<Sys>, &sys_kkt_solve<Sys>,
+                   &sys_host_kkt_solve<Sys>, &sys_ipm_solve<Sys>, &sys_host_ipm_solve<Sys>, &sys_rollout_cost<Sys>,
+                   &sys_host_rollout_cost<Sys>};
+}
+
+}  // namespace myr

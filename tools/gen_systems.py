@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Generate myriad_b200/csrc/systems_gen.cuh: per-system device functions (dynamics, running
+cost, their Jacobians and multiplier-contracted Hessians) from symbolic definitions.
+
+Each system below restates the formulas of the reference system it is named after (file:line
+cited per entry; table in SURVEY.md section 2.4).  sympy differentiates them and common
+sub-expression elimination produces straight-line fp64 code, so every kernel that needs
+f, [A|B] = df/d(x,u) or sum_i mu_i * hess f_i gets them without autodiff at run time.
+
+Run:  python tools/gen_systems.py   (writes the header; the header is committed)
+
+To add a system (the reference's "System plugin" extension point, myriad/systems/__init__.py:29-50):
+add an entry to SYSTEMS here, re-run, rebuild (python -c "import __graft_entry__ as g; g.build()"),
+and add the matching descriptor in myriad_b200/systems/__init__.py.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "myriad_b200", "csrc", "systems_gen.cuh")
+
+
+class Printer(C99CodePrinter):
+  def _print_Pow(self, expr):
+    b, e = expr.base, expr.exp
+    if e.is_Integer and 2 <= int(e) <= 4:
+      s = self.parenthesize(b, 100)  # force parens unless atom
+      return "(" + "*".join([s] * int(e)) + ")"
+    if e.is_Integer and -4 <= int(e) <= -1:
+      s = self.parenthesize(b, 100)
+      return "(1.0/(" + "*".join([s] * (-int(e))) + "))"
+    return super()._print_Pow(expr)
+
+  def _print_Rational(self, expr):
+    return f"({int(expr.p)}.0/{int(expr.q)}.0)"
+
+  def _print_Integer(self, expr):
+    return f"{int(expr)}.0"
+
+
+PR = Printer()
+
+
+def cc(e):
+  return PR.doprint(e)
+
+
+def X(n):
+  return sp.symbols(f"x0:{n}", real=True)
+
+
+def U(m):
+  return sp.symbols(f"u0:{m}", real=True)
+
+
+t = sp.Symbol("t", real=True)
+
+
+def system_defs():
+  """name -> dict(id, n, m, params [(name, default)], f(x,u,p), g(x,u,t,p), term(x,u,p) or None, ref)"""
+  S = {}
+
+  def add(name, sid, n, m, params, f, g, term=None, ref=""):
+    S[name] = dict(id=sid, n=n, m=m, params=params, f=f, g=g, term=term, ref=ref)
+
+  # myriad/systems/lenhart/simple_case.py:46-53
+  add("SIMPLECASE", 0, 1, 1, [("A", 1.0), ("B", 1.0), ("C", 4.0)],
+      lambda x, u, p: [-sp.Rational(1, 2) * x[0] ** 2 + p["C"] * u[0]],
+      lambda x, u, t, p: -p["A"] * x[0] + p["B"] * u[0] ** 2,
+      ref="myriad/systems/lenhart/simple_case.py:46-53")
+
+  # myriad/systems/classical_control/cartpole.py:76-87,106-108 (code, not docstring: SURVEY 9-1)
+  def cartpole_f(x, u, p):
+    g_, m1, m2, l = p["g"], p["m1"], p["m2"], p["length"]
+    th, dx, dth = x[1], x[2], x[3]
+    s, c = sp.sin(th), sp.cos(th)
+    ddx = (l * m2 * s * dth ** 2 + u[0] + m2 * g_ * c * s) / (m1 + m2 * (1 - c ** 2))
+    ddth = -(l * m2 * c * dth ** 2 + u[0] * c + (m1 + m2) * g_ * s) / (l * m1 + l * m2 * (1 - c ** 2))
+    return [dx, dth, ddx, ddth]
+
+  add("CARTPOLE", 1, 4, 1, [("g", 9.81), ("m1", 1.0), ("m2", 0.3), ("length", 0.5)],
+      cartpole_f, lambda x, u, t, p: u[0] ** 2,
+      ref="myriad/systems/classical_control/cartpole.py:76-87,106-108")
+
+  # myriad/systems/miscellaneous/van_der_pol.py:46-60
+  add("VANDERPOL", 2, 2, 1, [("a", 1.0)],
+      lambda x, u, p: [p["a"] * (1 - x[1] ** 2) * x[0] - x[1] + u[0], x[0]],
+      lambda x, u, t, p: x[0] ** 2 + x[1] ** 2 + u[0] ** 2,
+      ref="myriad/systems/miscellaneous/van_der_pol.py:46-60")
+
+  # myriad/systems/lenhart/cancer_treatment.py:62-76
+  add("CANCERTREATMENT", 3, 1, 1, [("r", 0.3), ("a", 3.0), ("delta", 0.45)],
+      lambda x, u, p: [p["r"] * x[0] * sp.log(1 / x[0]) - u[0] * p["delta"] * x[0]],
+      lambda x, u, t, p: p["a"] * x[0] ** 2 + u[0] ** 2,
+      ref="myriad/systems/lenhart/cancer_treatment.py:62-76")
+
+  # ---- further reference systems, smooth ones only
+  # myriad/systems/lenhart/mould_fungicide.py:50-66
+  add("MOULDFUNGICIDE", 4, 1, 1, [("r", 0.3), ("M", 10.0), ("A", 10.0)],
+      lambda x, u, p: [p["r"] * (p["M"] - x[0]) - u[0] * x[0]],
+      lambda x, u, t, p: p["A"] * x[0] ** 2 + u[0] ** 2,
+      ref="myriad/systems/lenhart/mould_fungicide.py:50-66")
+  # myriad/systems/lenhart/bioreactor.py:61-83
+  add("BIOREACTOR", 5, 1, 1, [("K", 2.0), ("G", 1.0), ("D", 1.0)],
+      lambda x, u, p: [p["G"] * u[0] * x[0] - p["D"] * x[0] ** 2],
+      lambda x, u, t, p: -p["K"] * x[0] + u[0],
+      ref="myriad/systems/lenhart/bioreactor.py:61-83")
+  # myriad/systems/lenhart/simple_case_with_bounds.py:49-56
+  add("SIMPLECASEWITHBOUNDS", 6, 1, 1, [("A", 1.0), ("C", 4.0)],
+      lambda x, u, p: [-sp.Rational(1, 2) * x[0] ** 2 + p["C"] * u[0]],
+      lambda x, u, t, p: -p["A"] * x[0] + u[0] ** 2,
+      ref="myriad/systems/lenhart/simple_case_with_bounds.py:49-56")
+  # myriad/systems/lenhart/glucose.py:72-104
+  add("GLUCOSE", 7, 2, 1, [("a", 1.0), ("b", 1.0), ("c", 1.0), ("A", 2.0), ("l", 0.5)],
+      lambda x, u, p: [-p["a"] * x[0] - p["b"] * x[1], -p["c"] * x[1] + u[0]],
+      lambda x, u, t, p: 100000 * (p["A"] * (x[0] - p["l"]) ** 2 + u[0] ** 2),
+      ref="myriad/systems/lenhart/glucose.py:72-104")
+  # myriad/systems/lenhart/harvest.py:55-62 (time-dependent cost)
+  add("HARVEST", 8, 1, 1, [("A", 5.0), ("k", 10.0), ("m", 0.2)],
+      lambda x, u, p: [-(p["m"] + u[0]) * x[0]],
+      lambda x, u, t, p: -p["A"] * (p["k"] * t / (t + 1)) * x[0] * u[0] + u[0] ** 2,
+      ref="myriad/systems/lenhart/harvest.py:55-62")
+  # myriad/systems/lenhart/timber_harvest.py:62-85 (time-dependent cost)
+  add("TIMBERHARVEST", 9, 1, 1, [("r", 0.0), ("k", 1.0)],
+      lambda x, u, p: [p["k"] * x[0] * u[0]],
+      lambda x, u, t, p: -sp.exp(-p["r"] * t) * x[0] * (1 - u[0]),
+      ref="myriad/systems/lenhart/timber_harvest.py:62-85")
+  return S
+
+
+def packed_index(i, j, nw):
+  if i > j:
+    i, j = j, i
+  return i * nw - (i * (i - 1)) // 2 + (j - i)
+
+
+def emit_block(lines, assigns, indent="    "):
+  """CSE over all right-hand sides and print; assigns = [(lhs_string, expr, op)] op in {'=', '+='}"""
+  exprs = [e for _, e, _ in assigns]
+  repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("v"), optimizations="basic")
+  # merge sin/cos pairs of the same argument into one sincos
+  done = set()
+  sc_pairs = {}
+  for sym, ex in repl:
+    if ex.func in (sp.sin, sp.cos):
+      sc_pairs.setdefault(ex.args[0], {})[ex.func] = sym
+  for sym, ex in repl:
+    if ex.func in (sp.sin, sp.cos) and len(sc_pairs.get(ex.args[0], {})) == 2:
+      arg = ex.args[0]
+      if arg in done:
+        continue
+      done.add(arg)
+      s_sym, c_sym = sc_pairs[arg][sp.sin], sc_pairs[arg][sp.cos]
+      lines.append(f"{indent}double {s_sym}, {c_sym}; sincos({cc(arg)}, &{s_sym}, &{c_sym});")
+    else:
+      lines.append(f"{indent}const double {sym} = {cc(ex)};")
+  for (lhs, _, op), ex in zip(assigns, red):
+    if op == "+=" and ex == 0:
+      continue
+    lines.append(f"{indent}{lhs} {op} {cc(ex)};")
+
+
+def gen_system(name, d):
+  n, m = d["n"], d["m"]
+  nw = n + m
+  x, u = X(n), U(m)
+  pn = [k for k, _ in d["params"]]
+  psym = {k: sp.Symbol(f"p_{k}", real=True) for k in pn}
+  f = [sp.sympify(e) for e in d["f"](x, u, psym)]
+  g = sp.sympify(d["g"](x, u, t, psym))
+  w = list(x) + list(u)
+  mu = sp.symbols(f"mu0:{n}", real=True)
+  wq = sp.Symbol("wq", real=True)
+  J = [[sp.diff(fi, wj) for wj in w] for fi in f]
+  L = sum(mu[i] * f[i] for i in range(n))
+  Hf = [[sp.diff(L, w[i], w[j]) for j in range(nw)] for i in range(nw)]
+  gg = [sp.diff(g, wj) for wj in w]
+  Hg = [[sp.diff(g, w[i], w[j]) for j in range(nw)] for i in range(nw)]
+  time_dep = g.has(t)
+
+  cls = name.title().replace("_", "")
+  out = []
+  out.append(f"// {name}: {d['ref']}")
+  out.append(f"struct Sys{cls} {{")
+  out.append(f"  static constexpr int id = {d['id']}, n = {n}, m = {m}, nw = {nw}, np = {len(pn)};")
+  out.append(f"  static constexpr bool time_dependent_cost = {'true' if time_dep else 'false'};")
+  out.append(f"  static constexpr const char* name = \"{name}\";")
+  out.append("  MYR_HD static void default_params(double* p) {")
+  for i, (k, v) in enumerate(d["params"]):
+    out.append(f"    p[{i}] = {v!r};  // {k}")
+  out.append("  }")
+
+  def prologue(lines, need_u=True, need_t=False):
+    for i in range(n):
+      lines.append(f"    const double x{i} = x[{i}];")
+    for i in range(m):
+      lines.append(f"    const double u{i} = u[{i}];")
+    for i, k in enumerate(pn):
+      lines.append(f"    const double p_{k} = p[{i}];")
+
+  def fn(sig, body_assigns, ret=None, pre=None):
+    lines = [f"  MYR_HD static {sig} {{"]
+    prologue(lines)
+    if pre:
+      lines += pre
+    emit_block(lines, body_assigns)
+    if ret:
+      lines.append(f"    return {ret};")
+    lines.append("  }")
+    # silence unused-variable warnings
+    lines.insert(1, "    (void)x; (void)u; (void)p;")
+    return lines
+
+  # f
+  out += fn("void f(const double* x, const double* u, const double* p, double* f)",
+            [(f"f[{i}]", f[i], "=") for i in range(n)])
+  # f + jac (row-major n x nw)
+  out += fn("void fjac(const double* x, const double* u, const double* p, double* f, double* J)",
+            [(f"f[{i}]", f[i], "=") for i in range(n)] +
+            [(f"J[{i * nw + j}]", J[i][j], "=") for i in range(n) for j in range(nw)])
+  # f + jac + H += sum mu_i hess f_i (packed upper, row-major)
+  mu_pre = [f"    const double mu{i} = mu[{i}];" for i in range(n)]
+  out += fn("void fjac_hess(const double* x, const double* u, const double* p, const double* mu, double* f, double* J, double* H)",
+            [(f"f[{i}]", f[i], "=") for i in range(n)] +
+            [(f"J[{i * nw + j}]", J[i][j], "=") for i in range(n) for j in range(nw)] +
+            [(f"H[{packed_index(i, j, nw)}]", Hf[i][j], "+=") for i in range(nw) for j in range(i, nw)],
+            pre=mu_pre)
+  # cost
+  out += fn("double cost(const double* x, const double* u, double t, const double* p)",
+            [("const double g_", g, "=")], ret="g_", pre=["    (void)t;"])
+  out += fn("double cost_grad(const double* x, const double* u, double t, const double* p, double* g)",
+            [("const double g_", g, "=")] + [(f"g[{j}]", gg[j], "=") for j in range(nw)], ret="g_", pre=["    (void)t;"])
+  out += fn("double cost_grad_hess(const double* x, const double* u, double t, const double* p, double wq, double* g, double* H)",
+            [("const double g_", g, "=")] + [(f"g[{j}]", gg[j], "=") for j in range(nw)] +
+            [(f"H[{packed_index(i, j, nw)}]", wq * Hg[i][j], "+=") for i in range(nw) for j in range(i, nw)],
+            ret="g_", pre=["    (void)t; (void)wq;"])
+  out.append("};")
+  out.append("")
+  return out
+
+
+def main():
+  S = system_defs()
+  lines = [
+    "// GENERATED by tools/gen_systems.py -- do not edit by hand.",
+    "// Per-system device functions: dynamics f(x,u), Jacobian J = df/d(x,u) (row-major n x (n+m)),",
+    "// multiplier-contracted Hessian H += sum_i mu_i * d2 f_i / d(x,u)^2 (packed upper triangle,",
+    "// row-major: idx(i,j) = i*nw - i*(i-1)/2 + (j-i)), running cost g(x,u,t) with gradient/Hessian.",
+    "#pragma once",
+    "#include <math.h>",
+    "#ifndef MYR_HD",
+    "#ifdef __CUDACC__",
+    "#define MYR_HD __host__ __device__ __forceinline__",
+    "#else",
+    "#define MYR_HD inline",
+    "#endif",
+    "#endif",
+    "",
+    "namespace myr {",
+    "",
+  ]
+  for name, d in S.items():
+    lines += gen_system(name, d)
+  # dispatch macro over all generated systems
+  lines.append("#define MYR_FOR_EACH_SYSTEM(X) \\")
+  names = list(S.keys())
+  for i, name in enumerate(names):
+    cls = name.title().replace("_", "")
+    lines.append(f"  X(Sys{cls})" + (" \\" if i + 1 < len(names) else ""))
+  lines.append("")
+  lines.append("}  // namespace myr")
+  os.makedirs(os.path.dirname(OUT), exist_ok=True)
+  with open(OUT, "w") as fh:
+    fh.write("\n".join(lines) + "\n")
+  print("wrote", OUT, len(lines), "lines")
+
+
+if __name__ == "__main__":
+  sys.exit(main())
