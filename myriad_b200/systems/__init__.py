@@ -1,0 +1,103 @@
+"""SystemType plugin surface (mirror of myriad/systems/__init__.py:29-53): enum members are callable
+constructors with the reference's constructor arguments and defaults."""
+from __future__ import annotations
+
+from enum import Enum
+
+import numpy as np
+
+from .base import FiniteHorizonControlSystem
+
+
+class SimpleCase(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/simple_case.py:25-53"""
+
+  def __init__(self, A=1., B=1., C=4., x_0=1., T=1.):
+    super().__init__(x_0=np.array([x_0], dtype=np.float64), x_T=None, T=T,
+                     bounds=np.array([[-np.inf, np.inf], [-np.inf, np.inf]]), terminal_cost=False, discrete=False,
+                     device_name="SIMPLECASE", params=[A, B, C])
+    self.A, self.B, self.C = A, B, C
+
+
+class CartPole(FiniteHorizonControlSystem):
+  """myriad/systems/classical_control/cartpole.py:50-73"""
+
+  def __init__(self, g: float = 9.81, m1: float = 1., m2: float = .3, length: float = 0.5):
+    self.m1, self.m2, self.length, self.g = m1, m2, length, g
+    self.u_max, self.d_max, self.d = 20, 2.0, 1.0
+    super().__init__(x_0=np.array([0., 0., 0., 0.]), x_T=np.array([self.d, np.pi, 0., 0.]), T=2.0,
+                     bounds=np.array([[-self.d_max, self.d_max], [-2 * np.pi, 2 * np.pi], [-5., 5.], [-10., 10.],
+                                      [-self.u_max, self.u_max]]),
+                     terminal_cost=False, device_name="CARTPOLE", params=[g, m1, m2, length])
+
+
+class VanDerPol(FiniteHorizonControlSystem):
+  """myriad/systems/miscellaneous/van_der_pol.py:29-44"""
+
+  def __init__(self, a=1.):
+    self.a = a
+    super().__init__(x_0=np.array([0., 1.]), x_T=np.zeros(2), T=10.0,
+                     bounds=np.array([[-4., 4.], [-4., 4.], [-0.75, 1.0]]), terminal_cost=False,
+                     device_name="VANDERPOL", params=[a])
+
+
+class CancerTreatment(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/cancer_treatment.py:40-60"""
+
+  def __init__(self, r=0.3, a=3., delta=0.45, x_0=0.975, T=20):
+    super().__init__(x_0=np.array([x_0], dtype=np.float64), x_T=None, T=T, bounds=np.array([[1e-3, 1.], [0., 2.]]),
+                     terminal_cost=False, discrete=False, device_name="CANCERTREATMENT", params=[r, a, delta])
+    self.r, self.a, self.delta = r, a, delta
+
+
+class MouldFungicide(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/mould_fungicide.py:29-48"""
+
+  def __init__(self, r=0.3, M=10., A=10., x_0=1.0, T=5):
+    super().__init__(x_0=np.array([x_0], dtype=np.float64), x_T=None, T=T, bounds=np.array([[0., 5.], [0., 5.]]),
+                     terminal_cost=False, discrete=False, device_name="MOULDFUNGICIDE", params=[r, M, A])
+
+
+class SimpleCaseWithBounds(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/simple_case_with_bounds.py:25-47"""
+
+  def __init__(self, A=1., C=4., M_1=-1., M_2=2., x_0=1., T=1.):
+    super().__init__(x_0=np.array([x_0], dtype=np.float64), x_T=None, T=T, bounds=np.array([[0., 3.], [M_1, M_2]]),
+                     terminal_cost=False, discrete=False, device_name="SIMPLECASEWITHBOUNDS", params=[A, C])
+
+
+class _NotOnDevice:
+  def __init__(self, name):
+    self.name = name
+
+  def __call__(self, *a, **k):
+    raise NotImplementedError(f"system {self.name} has no generated device code yet: add it to tools/gen_systems.py "
+                              "(DESIGN.md, 'what comes next')")
+
+
+class SystemType(Enum):
+  """Same member names as the reference enum; members without a device implementation raise on call."""
+  CARTPOLE = CartPole
+  VANDERPOL = VanDerPol
+  SEIR = _NotOnDevice("SEIR")
+  TUMOUR = _NotOnDevice("TUMOUR")
+  MOUNTAINCAR = _NotOnDevice("MOUNTAINCAR")
+  PENDULUM = _NotOnDevice("PENDULUM")
+  SIMPLECASE = SimpleCase
+  MOULDFUNGICIDE = MouldFungicide
+  BACTERIA = _NotOnDevice("BACTERIA")
+  SIMPLECASEWITHBOUNDS = SimpleCaseWithBounds
+  CANCERTREATMENT = CancerTreatment
+  EPIDEMICSEIRN = _NotOnDevice("EPIDEMICSEIRN")
+  HARVEST = _NotOnDevice("HARVEST")
+  HIVTREATMENT = _NotOnDevice("HIVTREATMENT")
+  BEARPOPULATIONS = _NotOnDevice("BEARPOPULATIONS")
+  GLUCOSE = _NotOnDevice("GLUCOSE")
+  TIMBERHARVEST = _NotOnDevice("TIMBERHARVEST")
+  BIOREACTOR = _NotOnDevice("BIOREACTOR")
+  PREDATORPREY = _NotOnDevice("PREDATORPREY")
+  INVASIVEPLANT = _NotOnDevice("INVASIVEPLANT")
+  ROCKETLANDING = _NotOnDevice("ROCKETLANDING")
+
+  def __call__(self, *args, **kwargs) -> FiniteHorizonControlSystem:
+    return self.value(*args, **kwargs)

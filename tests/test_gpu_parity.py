@@ -1,0 +1,206 @@
+"""GPU parity tests (run with -m gpu on the B200 box): CUDA path through the C ABI vs
+ (a) golden fixtures produced by the unmodified reference code (tests/golden, oracle/make_golden.py),
+ (b) the CPU oracle (oracle/), (c) the host twin of the same templates.
+Tolerances: K1 outputs 1e-12 relative (fp64, different summation order only); solved problems
+|obj - obj_ref| <= 1e-5 relative vs the reference's SLSQP run (SciPy default ftol 1e-6 is the limiting
+side), constraint violation <= 1e-8."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from tests.cases import CASES, load
+
+pytestmark = pytest.mark.gpu
+
+COLLOC = sorted(c for c, v in CASES.items() if v[1] == "COLLOCATION")
+SOLVED = [c for c in COLLOC if "sol_cost" in load(c)]
+
+
+def _tr(case):
+  from myriad_b200 import problems as PR
+  from myriad_b200.systems import SystemType
+  sysname, opt, quad, meth, intervals, cpi = CASES[case]
+  system = SystemType[sysname]()
+  optid = PR.TRAPEZOIDAL if quad == "TRAPEZOIDAL" else PR.HERMITE_SIMPSON
+  return PR.Transcription(system, optid, meth, intervals, cpi)
+
+
+def _eng(tr):
+  from myriad_b200.engine import Engine
+  return Engine(tr.desc())
+
+
+def _dev(a):
+  return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda().contiguous()
+
+
+@pytest.mark.parametrize("case", COLLOC)
+def test_k1_matches_reference_fixture(case):
+  from myriad_b200 import problems as PR
+  fx = load(case)
+  tr = _tr(case)
+  eng = _eng(tr)
+  z = _dev(np.stack([fx["z"], fx["guess"]]))
+  r = eng.eval(z)
+  torch.cuda.synchronize()
+  np.testing.assert_allclose(r.f.cpu().numpy(), [fx["obj_z"], fx["obj_guess"]], rtol=1e-12, atol=1e-14)
+  np.testing.assert_allclose(r.c.cpu().numpy(), np.stack([fx["con_z"], fx["con_guess"]]), rtol=1e-12, atol=1e-13)
+  np.testing.assert_allclose(r.grad[0].cpu().numpy(), fx["grad_z"], rtol=1e-12, atol=1e-13)
+  J = PR.dense_jacobian(tr, r.Jblk)[0].cpu().numpy()
+  np.testing.assert_allclose(J, fx["jac_z"], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("case", ["s_cartpole_trap_10", "s_vanderpol_hs_10", "s_cancer_trap_20"])
+def test_k1_hessian_blocks_match_oracle(case):
+  from myriad_b200 import problems as PR
+  from oracle import nlp
+  from oracle.systems import make_system
+  from oracle.transcription import make_transcription
+  sysname, opt, quad, meth, intervals, cpi = CASES[case]
+  fx = load(case)
+  tr = _tr(case)
+  eng = _eng(tr)
+  rng = np.random.default_rng(1)
+  lam = rng.standard_normal(tr.ncon)
+  r = eng.eval(_dev(fx["z"][None]), _dev(lam[None]), hessian=True)
+  H = nlp.lagrangian_hessian(make_transcription(make_system(sysname), opt, intervals, cpi, meth, quad), fx["z"], lam)
+  zidx, _, _ = PR.block_index_maps(tr)
+  Hb = r.Hblk[0].cpu().numpy()
+  nw = zidx.shape[1]
+  mask = np.ones_like(H, dtype=bool)
+  for q in range(zidx.shape[0]):
+    blk = H[np.ix_(zidx[q], zidx[q])]
+    iu = np.triu_indices(nw)
+    np.testing.assert_allclose(Hb[q], blk[iu], rtol=1e-11, atol=1e-12)
+    mask[np.ix_(zidx[q], zidx[q])] = False
+  assert np.abs(H[mask]).max() == 0.0  # Lagrangian Hessian is block diagonal per node
+
+
+@pytest.mark.parametrize("case", ["s_cartpole_trap_10", "s_vanderpol_hs_10", "c2_cartpole_trap_100"])
+def test_k2_kkt_solve_matches_dense_numpy(case):
+  from myriad_b200 import problems as PR
+  fx = load(case)
+  tr = _tr(case)
+  eng = _eng(tr)
+  rng = np.random.default_rng(2)
+  lam = rng.standard_normal(tr.ncon)
+  z = _dev(fx["z"][None])
+  r = eng.eval(z, _dev(lam[None]), hessian=True)
+  lb, ub = fx["bounds"][:, 0], fx["bounds"][:, 1]
+  fixed = lb == ub
+  sigma = rng.uniform(0.1, 2.0, tr.nvars)
+  sig_in = np.where(fixed, np.inf, sigma)
+  rhs_z = rng.standard_normal(tr.nvars)
+  rhs_c = rng.standard_normal(tr.ncon)
+  delta_w = 5.0  # large enough that the inertia is right for a random lambda
+  dz, dlam, ok = eng.kkt_solve(r.Hblk, r.Jblk, _dev(sig_in[None]), _dev(rhs_z[None]), _dev(rhs_c[None]), delta_w, 0.0)
+  torch.cuda.synchronize()
+  # dense reference
+  zidx, _, _ = PR.block_index_maps(tr)
+  nv, nc = tr.nvars, tr.ncon
+  H = np.zeros((nv, nv))
+  Hb = r.Hblk[0].cpu().numpy()
+  nw = zidx.shape[1]
+  iu = np.triu_indices(nw)
+  for q in range(zidx.shape[0]):
+    blk = np.zeros((nw, nw)); blk[iu] = Hb[q]; blk = blk + blk.T - np.diag(np.diag(blk))
+    H[np.ix_(zidx[q], zidx[q])] = blk
+  J = PR.dense_jacobian(tr, r.Jblk)[0].cpu().numpy()
+  fr = np.where(~fixed)[0]
+  K = np.block([[H[np.ix_(fr, fr)] + np.diag(sigma[fr] + delta_w), J[:, fr].T], [J[:, fr], np.zeros((nc, nc))]])
+  sol = np.linalg.solve(K, -np.concatenate([rhs_z[fr], rhs_c]))
+  ev = np.linalg.eigvalsh(K)
+  assert int(ok[0]) == int((ev < 0).sum() == nc)
+  dz_ref = np.zeros(nv); dz_ref[fr] = sol[:len(fr)]
+  scale = max(1.0, np.abs(sol).max())
+  np.testing.assert_allclose(dz[0].cpu().numpy(), dz_ref, atol=1e-9 * scale)
+  np.testing.assert_allclose(dlam[0].cpu().numpy(), sol[len(fr):], atol=1e-9 * scale)
+
+
+@pytest.mark.parametrize("case", SOLVED)
+def test_k3_solution_matches_reference_solve(case):
+  """Objective / feasibility parity with the reference's own solve() (SLSQP) on the same NLP and guess."""
+  fx = load(case)
+  tr = _tr(case)
+  eng = _eng(tr)
+  out = eng.ipm_solve(_dev(fx["guess"][None]), _dev(fx["bounds"][None, :, 0]), _dev(fx["bounds"][None, :, 1]))
+  torch.cuda.synchronize()
+  assert int(out["status"][0]) == 0, out
+  assert float(out["con_inf"][0]) <= 1e-8
+  obj = float(out["obj"][0])
+  ref = float(fx["sol_cost"])
+  assert abs(obj - ref) <= 1e-5 * max(1.0, abs(ref)), (obj, ref)
+  assert obj <= ref + 1e-7 * max(1.0, abs(ref))  # the IPM is converged tighter than SLSQP's ftol=1e-6
+
+
+@pytest.mark.parametrize("case", ["c2_cartpole_trap_100", "c2_cartpole_hs_100", "s_vanderpol_trap_20"])
+def test_device_matches_host_twin(case):
+  """Same templates compiled for host and device: same iteration count and (near) identical iterates."""
+  from myriad_b200 import _lib as ML
+  fx = load(case)
+  tr = _tr(case)
+  eng = _eng(tr)
+  out = eng.ipm_solve(_dev(fx["guess"][None]), _dev(fx["bounds"][None, :, 0]), _dev(fx["bounds"][None, :, 1]))
+  torch.cuda.synchronize()
+  s = eng.sizes
+  z0 = np.ascontiguousarray(fx["guess"][None]); lb = np.ascontiguousarray(fx["bounds"][None, :, 0]); ub = np.ascontiguousarray(fx["bounds"][None, :, 1])
+  zo = np.zeros((1, s.nvars)); lo = np.zeros((1, s.ncon)); zL = np.zeros((1, s.nvars)); zU = np.zeros((1, s.nvars))
+  obj = np.zeros(1); kkt = np.zeros(1); cinf = np.zeros(1); st = np.zeros(1, np.int32); it = np.zeros(1, np.int32)
+  ws = np.zeros(s.ipm_workspace_doubles)
+  p = lambda a: a.ctypes.data_as(C.c_void_p)
+  o = ML.MyrIpmOpts()
+  ML.check(ML.lib().myr_host_ipm_solve(C.byref(eng.desc), C.byref(o), 1, p(z0), p(lb), p(ub), p(zo), p(lo), p(zL), p(zU), p(obj), p(kkt),
+                                       p(cinf), p(st), p(it), p(ws), ws.size))
+  assert int(out["status"][0]) == int(st[0]) == 0
+  assert int(out["iters"][0]) == int(it[0])
+  np.testing.assert_allclose(float(out["obj"][0]), obj[0], rtol=1e-10)
+  np.testing.assert_allclose(out["z"][0].cpu().numpy(), zo[0], atol=1e-7)
+
+
+def test_batch_of_random_starts_cartpole():
+  """C2-shaped batch: instance 0 is the reference problem; every instance must satisfy the KKT conditions."""
+  from myriad_b200 import problems as PR
+  tr = _tr("c2_cartpole_trap_100")
+  eng = _eng(tr)
+  B = 256
+  x0 = PR.sample_x0(tr.system, B, device="cuda")
+  z0, lb, ub = PR.build_batch(tr, x0)
+  fx = load("c2_cartpole_trap_100")
+  np.testing.assert_allclose(z0[0].cpu().numpy(), fx["guess"], rtol=1e-13, atol=1e-15)
+  assert np.array_equal(lb[0].cpu().numpy(), fx["bounds"][:, 0]) and np.array_equal(ub[0].cpu().numpy(), fx["bounds"][:, 1])
+  out = eng.ipm_solve(z0, lb, ub)
+  torch.cuda.synchronize()
+  st = out["status"].cpu().numpy()
+  assert (st == 0).mean() >= 0.95, np.unique(st, return_counts=True)
+  ok = st == 0
+  assert float(out["con_inf"][torch.as_tensor(ok).cuda()].max()) <= 1e-8
+  # size-independent property: re-evaluating the returned point reproduces the reported objective/feasibility
+  r = eng.eval(out["z"])
+  np.testing.assert_allclose(r.f.cpu().numpy()[ok], out["obj"].cpu().numpy()[ok], rtol=1e-12)
+  assert float(r.c.abs().max(dim=1).values[torch.as_tensor(ok).cuda()].max()) <= 1e-8
+  # a single-instance solve of row 0 gives the same answer as inside the batch
+  single = eng.ipm_solve(z0[:1].clone(), lb[:1].clone(), ub[:1].clone())
+  assert torch.equal(single["z"][0], out["z"][0])
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_rollout_matches_reference_fixture(case):
+  from myriad_b200 import problems as PR
+  from myriad_b200.engine import Engine
+  from myriad_b200.systems import SystemType
+  fx = load(case)
+  if "rollout_states" not in fx or not np.isfinite(fx["rollout_states"]).all():
+    pytest.skip("no finite reference rollout for this combination")
+  sysname, opt, quad, meth, intervals, cpi = CASES[case]
+  system = SystemType[sysname]()
+  optid = PR.SHOOTING if opt == "SHOOTING" else (PR.TRAPEZOIDAL if quad == "TRAPEZOIDAL" else PR.HERMITE_SIMPSON)
+  tr = PR.Transcription(system, optid, meth, intervals, cpi)
+  eng = Engine.__new__(Engine)
+  eng.desc = tr.desc(); eng._ws = None
+  _, u = tr.unravel(fx["z"])
+  xs, cost = Engine.rollout_cost(eng, _dev(u[None]), _dev(np.asarray(system.x_0)[None]))
+  torch.cuda.synchronize()
+  np.testing.assert_allclose(xs[0].cpu().numpy(), fx["rollout_states"], rtol=1e-12, atol=1e-13)
+  np.testing.assert_allclose(float(cost[0]), float(fx["rollout_cost"]), rtol=1e-12)
