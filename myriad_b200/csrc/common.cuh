@@ -102,7 +102,7 @@ MYR_HDI double nanmax(double a, double b) { return (a != a || b != b) ? NAN : fm
 // mask bit i set => variable i is eliminated (fixed): it is skipped, its row/col of inv are zero and it
 // does not count in the inertia.  Bunch-Parlett: complete pivoting with 1x1 / 2x2 pivots.
 template <int N>
-__host__ __device__ inline void sym_inverse_inertia(double* A, uint32_t mask, double* inv, int& npos, int& nneg, int& nzero) {
+__host__ __device__ __noinline__ void sym_inverse_inertia(double* A, uint32_t mask, double* inv, int& npos, int& nneg, int& nzero) {
   int perm[N];   // perm[k] = original index placed at position k (active ones first)
   int na = 0;
 #pragma unroll
@@ -205,6 +205,92 @@ __host__ __device__ inline void sym_inverse_inertia(double* A, uint32_t mask, do
     }
     for (int i = 0; i < na; ++i) inv[perm[p2[i]] * N + perm[col]] = y[i];
   }
+}
+
+
+// Fast path: LDL^T in natural order (no pivoting), everything in registers (static indexing, fully unrolled).
+// Valid whenever no pivot is small relative to the block's scale; otherwise returns false and the caller falls
+// back to the pivoted Bunch-Parlett routine above.  Masked (fixed) variables are decoupled before factorising
+// and their rows/cols of the inverse are zero.  A: full symmetric N x N (not modified).
+template <int N>
+MYR_HDI bool sym_inverse_inertia_fast(const double* A, uint32_t mask, double* inv, int& npos, int& nneg) {
+  double a[N][N];
+  double scale = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const bool mi = (mask >> i) & 1u, mj = (mask >> j) & 1u;
+      const double v = (mi || mj) ? ((i == j) ? 1.0 : 0.0) : A[i * N + j];
+      a[i][j] = v;
+      scale = fmax(scale, fabs(v));
+    }
+  const double thresh = 1e-7 * scale;
+  double d[N], l[N][N];
+  bool ok = true;
+  int np_ = 0, nn_ = 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double dk = a[k][k];
+#pragma unroll
+    for (int j = 0; j < k; ++j) dk -= l[k][j] * l[k][j] * d[j];
+    d[k] = dk;
+    ok = ok && (fabs(dk) > thresh);
+    const bool masked = (mask >> k) & 1u;
+    if (!masked) { if (dk > 0) ++np_; else ++nn_; }
+    const double rk = 1.0 / dk;
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      double v = a[i][k];
+#pragma unroll
+      for (int j = 0; j < k; ++j) v -= l[i][j] * l[k][j] * d[j];
+      l[i][k] = v * rk;
+    }
+  }
+  if (!ok) return false;
+  // Linv (unit lower): m = L^-1
+  double m[N][N];
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+#pragma unroll
+    for (int i = c + 1; i < N; ++i) {
+      double v = -l[i][c];
+#pragma unroll
+      for (int j = c + 1; j < i; ++j) v -= l[i][j] * m[j][c];
+      m[i][c] = v;
+    }
+  }
+  // inv = m^T D^-1 m
+  double rd[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) rd[k] = 1.0 / d[k];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = i; j < N; ++j) {
+      // sum over k >= max(i,j)=j: m[k][i] * rd[k] * m[k][j], with m[k][k] = 1
+      double v = 0.0;
+#pragma unroll
+      for (int k = j; k < N; ++k) {
+        const double mki = (k == i) ? 1.0 : m[k][i];
+        const double mkj = (k == j) ? 1.0 : m[k][j];
+        v += mki * rd[k] * mkj;
+      }
+      const bool mi = (mask >> i) & 1u, mj = (mask >> j) & 1u;
+      v = (mi || mj) ? 0.0 : v;
+      inv[i * N + j] = v;
+      inv[j * N + i] = v;
+    }
+  npos = np_; nneg = nn_;
+  return true;
+}
+
+// inverse + inertia: fast path first, pivoted fallback
+template <int N>
+MYR_HDI void sym_inverse(double* A, uint32_t mask, double* inv, int& npos, int& nneg, int& nzero) {
+  nzero = 0;
+  if (sym_inverse_inertia_fast<N>(A, mask, inv, npos, nneg)) return;
+  sym_inverse_inertia<N>(A, mask, inv, npos, nneg, nzero);
 }
 
 }  // namespace myr

@@ -178,7 +178,7 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
 #pragma unroll
       for (int k = 0; k < BB; ++k) A[k] = D[i * BB + k];
       int p_, n_, z_;
-      sym_inverse_inertia<NC>(A, 0u, Dinv, p_, n_, z_);
+      sym_inverse<NC>(A, 0u, Dinv, p_, n_, z_);
       cp += p_; cn += n_; cz += z_;
       // VL = Dinv * U_{i-s}^T
       const double* Ul = U + (i - s) * BB;
@@ -286,7 +286,7 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
 #pragma unroll
     for (int k = 0; k < BB; ++k) A[k] = D[k];
     int p_, n_, z_;
-    sym_inverse_inertia<NC>(A, 0u, Dinv, p_, n_, z_);
+    sym_inverse<NC>(A, 0u, Dinv, p_, n_, z_);
     cp += p_; cn += n_; cz += z_;
 #pragma unroll
     for (int r = 0; r < NC; ++r) {
@@ -356,7 +356,7 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
 #pragma unroll
     for (int i = 0; i < NW; ++i) A[i * NW + i] += sigma[q * NW + i] + delta_w;
     int p_, n_, z_;
-    sym_inverse_inertia<NW>(A, fixmask[q], inv, p_, n_, z_);
+    sym_inverse<NW>(A, fixmask[q], inv, p_, n_, z_);
     hp += p_; hn += n_; hz += z_;
 #pragma unroll
     for (int i = 0; i < NW * NW; ++i) w[L.Hinv + q * NW * NW + i] = inv[i];
