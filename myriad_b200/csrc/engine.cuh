@@ -3,7 +3,10 @@
 // inertia) and K3 (primal-dual interior-point iteration).  One CTA works on one problem instance;
 // threads stride over nodes / stages.  Written once for device and host (see common.cuh).
 #pragma once
+#include <type_traits>
+
 #include "schemes.cuh"
+#include "shooting.cuh"
 
 namespace myr {
 
@@ -21,12 +24,19 @@ struct IpmOpts {
 
 enum Status : int { ST_SOLVED = 0, ST_ACCEPTABLE = 1, ST_MAXITER = -1, ST_LINESEARCH = -2, ST_INERTIA = -3, ST_NAN = -13 };
 
+// schemes whose internal NLP differs from the reference's (lifted shooting) declare kLifted
+template <class S, class = void>
+struct scheme_is_lifted { static constexpr bool value = false; };
+template <class S>
+struct scheme_is_lifted<S, typename std::enable_if<S::kLifted>::type> { static constexpr bool value = true; };
+
 // ------------------------------------------------------------------ workspace layout (doubles / instance)
 template <class S>
 struct Layout {
   int Q, St;
   int G, F, W, Hinv, gl, phi, psi, rb, dz, dzL, dzU, c, dlam;
   int crD, crU, crVL, crVU, crb, crx;
+  int ext;
   int total;
   MYR_HDI explicit Layout(const Problem& P) {
     Q = S::num_nodes(P); St = S::num_stages(P);
@@ -50,6 +60,9 @@ struct Layout {
     crVU = o; o += St * S::NC * S::NC;
     crb = o; o += St * S::NC;
     crx = dlam;  // CR writes its solution straight into dlam
+    // lifted schemes keep their internal iterate / bounds / multipliers in the workspace too
+    ext = o;
+    if (scheme_is_lifted<S>::value) o += 6 * Q * S::NW + St * S::NC;
     total = (o + 15) & ~15;
   }
   // doubles of the CR scratch (D,U,VL,VU,b), contiguous from crD
@@ -475,21 +488,31 @@ struct IpmIO {
   long long work_stride;
 };
 
+// per-instance pointers of the NLP the IPM iterates on (the reference NLP itself for collocation, the lifted one for
+// shooting); nv / ncn are that NLP's sizes
+struct InstPtrs {
+  const double* z0; const double* lb; const double* ub;
+  double* z; double* lam; double* zL; double* zU;
+  double* w;
+  int nv, ncn;
+};
+struct InstResult { double f, E0, cinf; int status, iters; };
+
 template <class S>
-MYR_HDI void ipm_solve_instance(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, double* cr, double* red,
-                                double* sig_sh /*Q*NW doubles*/, uint32_t* fix_sh /*Q*/) {
+MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const InstPtrs& ip, double* cr, double* red,
+                                      double* sig_sh /*Q*NW doubles*/, uint32_t* fix_sh /*Q*/) {
   constexpr int NW = S::NW, NC = S::NC;
   const Layout<S> L(P);
   const int Q = L.Q, St = L.St;
-  const int nv = P.nvars, ncn = P.ncon;
-  double* w = io.work + (long long)b * io.work_stride;
-  double* z = io.z + (long long)b * nv;
-  double* lam = io.lam + (long long)b * ncn;
-  double* zL = io.zL + (long long)b * nv;
-  double* zU = io.zU + (long long)b * nv;
-  const double* lb = io.lb + (long long)b * nv;
-  const double* ub = io.ub + (long long)b * nv;
-  const double* z0 = io.z0 + (long long)b * nv;
+  const int ncn = ip.ncn;
+  double* w = ip.w;
+  double* z = ip.z;
+  double* lam = ip.lam;
+  double* zL = ip.zL;
+  double* zU = ip.zU;
+  const double* lb = ip.lb;
+  const double* ub = ip.ub;
+  const double* z0 = ip.z0;
 
   // ---- initial point: push into the (relaxed) box, unit bound multipliers, zero lambda
   for (int q = MYR_TID; q < Q; q += MYR_NT) {
@@ -581,9 +604,12 @@ MYR_HDI void ipm_solve_instance(const Problem& P, const IpmOpts& O, const IpmIO&
     suml = block_sum(suml, red);
     const double sd = fmax(O.s_max, (suml + sumz) / fmax(1.0, (double)ncn + nbnd)) / O.s_max;
     const double sc = nbnd > 0 ? fmax(O.s_max, sumz / nbnd) / O.s_max : 1.0;
+    // lifted shooting: step defects accumulate along an interval's rollout, so the per-step feasibility tolerance is
+    // tightened by cpi to keep the REFERENCE constraint px_k - x_{k+1} within tol
+    const double cscale = scheme_is_lifted<S>::value ? (double)P.cpi : 1.0;
     auto Emu = [&](double m_) {
       const double comp = nbnd > 0 ? fmax(szmax - m_, m_ - szmin) / sc : 0.0;
-      return fmax(fmax(rdmax / sd, cinf), comp);
+      return fmax(fmax(rdmax / sd, cinf * cscale), comp);
     };
     E0 = Emu(0.0);
     if (!(E0 == E0) || !isfinite(f)) { status = ST_NAN; break; }
@@ -746,12 +772,105 @@ MYR_HDI void ipm_solve_instance(const Problem& P, const IpmOpts& O, const IpmIO&
     MYR_SYNC();
     ++it;
   }
+  InstResult res;
+  res.f = f; res.E0 = E0; res.cinf = cinf; res.status = status; res.iters = it;
+  return res;
+}
+
+// Collocation: the IPM works directly on the caller's arrays.
+template <class S>
+MYR_HDI typename std::enable_if<!scheme_is_lifted<S>::value>::type
+ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, double* cr, double* red, double* sig_sh, uint32_t* fix_sh) {
+  const long long nv = P.nvars, nc = P.ncon;
+  InstPtrs ip{io.z0 + b * nv, io.lb + b * nv, io.ub + b * nv, io.z + b * nv, io.lam + b * nc, io.zL + b * nv, io.zU + b * nv,
+              io.work + (long long)b * io.work_stride, P.nvars, P.ncon};
+  const InstResult r = ipm_solve_instance<S>(P, O, ip, cr, red, sig_sh, fix_sh);
   if (MYR_TID == 0) {
-    io.obj[b] = f;
-    io.kkt_err[b] = E0;
-    io.con_inf[b] = cinf;
-    io.status[b] = status;
-    io.iters[b] = it;
+    io.obj[b] = r.f; io.kkt_err[b] = r.E0; io.con_inf[b] = r.cinf; io.status[b] = r.status; io.iters[b] = r.iters;
+  }
+}
+
+// Lifted shooting: expand the reference NLP data into the lifted NLP, solve, map the solution back and report the
+// objective / constraint violation of the REFERENCE NLP (rollouts from the interval-start states).
+template <class S>
+MYR_HDI typename std::enable_if<scheme_is_lifted<S>::value>::type
+ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, double* cr, double* red, double* sig_sh, uint32_t* fix_sh) {
+  constexpr int n = S::n, m = S::m, NW = S::NW, NC = S::NC;
+  const Layout<S> L(P);
+  const int Q = L.Q, St = L.St;
+  const int nvI = Q * NW, ncI = St * NC;
+  const long long nv = P.nvars, nc = P.ncon;
+  double* w = io.work + (long long)b * io.work_stride;
+  double* zI0 = w + L.ext; double* lbI = zI0 + nvI; double* ubI = lbI + nvI; double* zI = ubI + nvI;
+  double* zLI = zI + nvI; double* zUI = zLI + nvI; double* lamI = zUI + nvI;
+  const double* z0 = io.z0 + b * nv; const double* lb = io.lb + b * nv; const double* ub = io.ub + b * nv;
+  // ---- expansion: real variables copy guess and bounds; copies / hidden states are free
+  for (int q = MYR_TID; q < Q; q += MYR_NT) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      const int r = S::ref_index(P, q, i);
+      double g0 = 0.0, l0 = -INFINITY, u0 = INFINITY;
+      if (r >= 0) { g0 = z0[r]; l0 = lb[r]; u0 = ub[r]; }
+      else if (i >= n && q + 1 < Q) {  // control copy: value of the next node's first control
+        const int r2 = S::ref_index(P, q + 1, n + (i - n) % m);
+        g0 = z0[r2];
+      }
+      if (S::is_dead(P, q, i)) { l0 = g0; u0 = g0; }
+      zI0[q * NW + i] = g0; lbI[q * NW + i] = l0; ubI[q * NW + i] = u0;
+    }
+  }
+  MYR_SYNC();
+  // hidden states: roll the guess out inside every interval (what the reference's first constraint evaluation does)
+  for (int k = MYR_TID; k < P.N; k += MYR_NT) {
+    double s[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) s[i] = zI0[(k * P.cpi) * NW + i];
+    for (int j = 0; j + 1 < P.cpi; ++j) {
+      const int q = k * P.cpi + j;
+      double v[NW], ell, gl[1], phi[NC], psi[NC], Gm[1], Fm[1], Wd[1], l0[NC];
+#pragma unroll
+      for (int i = 0; i < n; ++i) v[i] = s[i];
+#pragma unroll
+      for (int i = n; i < NW; ++i) v[i] = zI0[q * NW + i];
+#pragma unroll
+      for (int r = 0; r < NC; ++r) l0[r] = 0.0;
+      S::template eval_node<0>(P, q, v, l0, l0, ell, gl, phi, psi, Gm, Fm, Wd);
+#pragma unroll
+      for (int i = 0; i < n; ++i) { s[i] = phi[i]; zI0[(q + 1) * NW + i] = phi[i]; }
+    }
+  }
+  MYR_SYNC();
+  Problem Pi = P;
+  Pi.nvars = nvI; Pi.ncon = ncI;
+  InstPtrs ip{zI0, lbI, ubI, zI, lamI, zLI, zUI, w, nvI, ncI};
+  InstResult r = ipm_solve_instance<S>(Pi, O, ip, cr, red, sig_sh, fix_sh);
+  MYR_SYNC();
+  // ---- map back
+  double* z = io.z + b * nv; double* lam = io.lam + b * nc; double* zL = io.zL + b * nv; double* zU = io.zU + b * nv;
+  for (int q = MYR_TID; q < Q; q += MYR_NT) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      const int rr = S::ref_index(P, q, i);
+      if (rr >= 0) { z[rr] = zI[q * NW + i]; zL[rr] = zLI[q * NW + i]; zU[rr] = zUI[q * NW + i]; }
+    }
+  }
+  for (int k = MYR_TID; k < P.N; k += MYR_NT)
+#pragma unroll
+    for (int i = 0; i < n; ++i) lam[k * n + i] = lamI[((k + 1) * P.cpi - 1) * NC + i];
+  MYR_SYNC();
+  // objective and constraint violation as the reference defines them (shooting.py:169-241)
+  double fs = 0.0, cm = 0.0;
+  for (int k = MYR_TID; k < P.N; k += MYR_NT) {
+    double px[n], cst;
+    ShootingInterval<typename S::System, (NW - n) / m>::template run<false>(P, k, z, px, cst, nullptr, 0);
+    fs += cst;
+#pragma unroll
+    for (int i = 0; i < n; ++i) { const double d = px[i] - z[(k + 1) * n + i]; cm = fmax(cm, (d != d) ? INFINITY : fabs(d)); }
+  }
+  fs = block_sum(fs, red);
+  cm = block_max(cm, red);
+  if (MYR_TID == 0) {
+    io.obj[b] = fs; io.kkt_err[b] = r.E0; io.con_inf[b] = cm; io.status[b] = r.status; io.iters[b] = r.iters;
   }
 }
 

@@ -56,12 +56,32 @@ static int dispatch_scheme(const MyrDesc* d, int B, F&& fn) {
       return fn(S{}, P);
     }
     case MYR_OPT_SHOOTING:
-      return fail(MYR_E_UNSUPPORTED, "SHOOTING block kernels are not built yet for %s", Sys::name);
+      return fail(MYR_E_UNSUPPORTED, "this entry point has no SHOOTING block form (%s); use myr_eval / myr_ipm_solve", Sys::name);
     default:
       return fail(MYR_E_BADARG, "unknown optimizer %s%lld", "", d->optimizer);
   }
 }
 
+// shooting: lifted scheme selected by the number of control slots per step
+template <class Sys, class F>
+static int dispatch_shooting(const MyrDesc* d, int B, F&& fn) {
+  Problem P;
+  int rc = make_problem<Sys>(d, B, P);
+  if (rc) return rc;
+  if (d->optimizer != MYR_OPT_SHOOTING) return fail(MYR_E_BADARG, "not a shooting descriptor%s", "");
+  P.h = P.T / (P.N * P.cpi);
+  if (P.method == EULER) { using S = ShootingLifted<Sys, 1>; P.nvars = S::nvars(P); P.ncon = S::ncon(P); return fn(S{}, P); }
+  if (P.method == RK4) { using S = ShootingLifted<Sys, 3>; P.nvars = S::nvars(P); P.ncon = S::ncon(P); return fn(S{}, P); }
+  using S = ShootingLifted<Sys, 2>; P.nvars = S::nvars(P); P.ncon = S::ncon(P);
+  return fn(S{}, P);
+}
+
+// any optimizer (entry points that work for all three transcriptions)
+template <class Sys, class F>
+static int dispatch_any(const MyrDesc* d, int B, F&& fn) {
+  if (d->optimizer == MYR_OPT_SHOOTING) return dispatch_shooting<Sys>(d, B, fn);
+  return dispatch_scheme<Sys>(d, B, fn);
+}
 
 static int cuda_check(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -78,30 +98,72 @@ static int threads_for(int Q) {
 
 template <class Sys>
 int sys_problem_sizes(const MyrDesc* desc, MyrSizes* out) {
-  if (desc->optimizer == MYR_OPT_SHOOTING) {
-    Problem P;
-    int rc = make_problem<Sys>(desc, 0, P);
-    if (rc) return rc;
-    const int mc = P.method == RK4 ? 2 : 1;
-    out->n = Sys::n; out->m = Sys::m;
-    out->nx_nodes = P.N + 1; out->nu_nodes = mc * P.N * P.cpi + 1;
-    out->nvars = out->nx_nodes * Sys::n + out->nu_nodes * Sys::m;
-    out->ncon = P.N * Sys::n;
-    return (int)MYR_OK;
-  }
-  return dispatch_scheme<Sys>(desc, 0, [&](auto s, const Problem& P) {
+  return dispatch_any<Sys>(desc, 0, [&](auto s, const Problem& P) {
     using S = decltype(s);
     const Layout<S> L(P);
     out->n = S::n; out->m = S::m;
-    out->nx_nodes = out->nu_nodes = L.Q;
     out->nvars = P.nvars; out->ncon = P.ncon;
     out->nodes = L.Q; out->stages = L.St; out->nw = S::NW; out->nc = S::NC;
-    out->stage_nodes = S::kMaxStageNodes;
-    out->jac_block_doubles = (int64_t)L.St * S::kMaxStageNodes * S::NC * S::NW;
-    out->hess_block_doubles = (int64_t)L.Q * S::NWP;
     out->ipm_workspace_doubles = L.total;
+    if (scheme_is_lifted<S>::value) {
+      const int mc = P.method == RK4 ? 2 : 1;
+      out->nx_nodes = P.N + 1; out->nu_nodes = mc * P.N * P.cpi + 1;
+      out->stage_nodes = 1;
+      // per interval: (n + 1) rows x (n + (mc*cpi+1) m) columns; row n is the gradient of the interval's cost
+      out->jac_block_doubles = (int64_t)P.N * (S::n + 1) * (S::n + (mc * P.cpi + 1) * S::m);
+      out->hess_block_doubles = 0;
+    } else {
+      out->nx_nodes = out->nu_nodes = L.Q;
+      out->stage_nodes = S::kMaxStageNodes;
+      out->jac_block_doubles = (int64_t)L.St * S::kMaxStageNodes * S::NC * S::NW;
+      out->hess_block_doubles = (int64_t)L.Q * S::NWP;
+    }
     return (int)MYR_OK;
   });
+}
+
+// Shooting K1 (reference-level): one thread per (instance, interval) rolls the interval out with forward-mode
+// sensitivities.  Jblk[b][k] is (n+1) x ncol row-major: rows 0..n-1 = d px_k / d (xs[k], interval controls), row n =
+// gradient of the interval's integrated cost; c = px - xs[k+1]; f and grad are accumulated with atomics.
+template <class Sys, int NU>
+MYR_HDI void shooting_eval_pair(const Problem& P, long long pair, const double* z_all, double* f, double* grad, double* c, double* J,
+                                double* scratch_row) {
+  using SI = ShootingInterval<Sys, NU>;
+  constexpr int n = Sys::n, m = Sys::m;
+  const int b = (int)(pair / P.N), k = (int)(pair % P.N);
+  const int M = SI::mc * P.cpi, ncol = n + (M + 1) * m;
+  const double* z = z_all + (long long)b * P.nvars;
+  double px[n], cst;
+  double* S = J ? J + ((long long)b * P.N + k) * (n + 1) * ncol : scratch_row;
+  if (S) SI::template run<true>(P, k, z, px, cst, S, ncol);
+  else SI::template run<false>(P, k, z, px, cst, nullptr, 0);
+  if (c) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) c[(long long)b * P.ncon + k * n + i] = px[i] - z[(k + 1) * n + i];
+  }
+#ifdef __CUDA_ARCH__
+  if (f) atomicAdd(f + b, cst);
+#else
+  if (f) f[b] += cst;
+#endif
+  if (grad && S) {
+    double* g = grad + (long long)b * P.nvars;
+    const int ubase = (P.N + 1) * n;
+    for (int col = 0; col < ncol; ++col) {
+      const int dst = col < n ? k * n + col : ubase + k * M * m + (col - n);
+#ifdef __CUDA_ARCH__
+      atomicAdd(g + dst, S[n * ncol + col]);
+#else
+      g[dst] += S[n * ncol + col];
+#endif
+    }
+  }
+}
+
+template <class Sys, int NU>
+__global__ void shooting_eval_kernel(Problem P, const double* z, double* f, double* grad, double* c, double* J) {
+  const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair < (long long)P.B * P.N) shooting_eval_pair<Sys, NU>(P, pair, z, f, grad, c, J, nullptr);
 }
 
 // ------------------------------------------------------------------ K1 kernel
@@ -267,6 +329,22 @@ __global__ void __launch_bounds__(256) eval_kernel(Problem P, const double* __re
 template <class Sys>
 int sys_eval(const MyrDesc* desc, int B, const double* z, const double* lam, double* f, double* grad, double* c,
                         double* Jblk, double* Hblk, void* stream) {
+  if (desc->optimizer == MYR_OPT_SHOOTING) {
+    return dispatch_shooting<Sys>(desc, B, [&](auto s, const Problem& P) {
+      using S = decltype(s);
+      constexpr int NU = (S::NW - S::n) / S::m;
+      if (B == 0) return (int)MYR_OK;
+      if (!z) return fail(MYR_E_BADARG, "z is null%s", "");
+      if (Hblk) return fail(MYR_E_UNSUPPORTED, "no reference-level Hessian blocks for SHOOTING (%s)", Sys::name);
+      if (grad && !Jblk) return fail(MYR_E_BADARG, "SHOOTING grad needs Jblk (the cost row lives there)%s", "");
+      cudaStream_t st = (cudaStream_t)stream;
+      if (f) cudaMemsetAsync(f, 0, sizeof(double) * B, st);
+      if (grad) cudaMemsetAsync(grad, 0, sizeof(double) * (size_t)B * P.nvars, st);
+      const long long pairs = (long long)B * P.N;
+      shooting_eval_kernel<Sys, NU><<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>(P, z, f, grad, c, Jblk);
+      return cuda_check("myr_eval(shooting)");
+    });
+  }
   return dispatch_scheme<Sys>(desc, B, [&](auto s, const Problem& P) {
     using S = decltype(s);
     if (B == 0) return (int)MYR_OK;
@@ -284,6 +362,18 @@ int sys_eval(const MyrDesc* desc, int B, const double* z, const double* lam, dou
 template <class Sys>
 int sys_host_eval(const MyrDesc* desc, int B, const double* z, const double* lam, double* f, double* grad, double* c,
                              double* Jblk, double* Hblk) {
+  if (desc->optimizer == MYR_OPT_SHOOTING) {
+    return dispatch_shooting<Sys>(desc, B, [&](auto s, const Problem& P) {
+      using S = decltype(s);
+      constexpr int NU = (S::NW - S::n) / S::m;
+      if (Hblk) return fail(MYR_E_UNSUPPORTED, "no reference-level Hessian blocks for SHOOTING (%s)", Sys::name);
+      if (grad && !Jblk) return fail(MYR_E_BADARG, "SHOOTING grad needs Jblk (the cost row lives there)%s", "");
+      if (f) for (int b = 0; b < B; ++b) f[b] = 0.0;
+      if (grad) for (long long i = 0; i < (long long)B * P.nvars; ++i) grad[i] = 0.0;
+      for (long long pair = 0; pair < (long long)B * P.N; ++pair) shooting_eval_pair<Sys, NU>(P, pair, z, f, grad, c, Jblk, nullptr);
+      return (int)MYR_OK;
+    });
+  }
   return dispatch_scheme<Sys>(desc, B, [&](auto s, const Problem& P) {
     using S = decltype(s);
     const int Q = S::num_nodes(P);
@@ -428,7 +518,7 @@ __global__ void __launch_bounds__(256) ipm_kernel(Problem P, IpmOpts O, IpmIO io
   double* crs = reinterpret_cast<double*>(reinterpret_cast<char*>(fix) + ((((size_t)L.Q * sizeof(uint32_t)) + 15) & ~(size_t)15));
   for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
     double* cr = cr_in_smem ? crs : io.work + (long long)b * io.work_stride + L.crD;
-    ipm_solve_instance<S>(P, O, io, b, cr, red, sig, fix);
+    ipm_solve_entry<S>(P, O, io, b, cr, red, sig, fix);
     __syncthreads();
   }
 }
@@ -437,7 +527,7 @@ template <class Sys>
 int sys_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const double* z0, const double* lb, const double* ub, double* z,
                              double* lam, double* zL, double* zU, double* obj, double* kkt_err, double* con_inf, int32_t* status, int32_t* iters,
                              double* ws, size_t ws_doubles, void* stream) {
-  return dispatch_scheme<Sys>(desc, B, [&](auto s, const Problem& P) {
+  return dispatch_any<Sys>(desc, B, [&](auto s, const Problem& P) {
     using S = decltype(s);
     if (B == 0) return (int)MYR_OK;
     if (!z0 || !lb || !ub || !z || !lam || !zL || !zU || !obj || !kkt_err || !con_inf || !status || !iters || !ws)
@@ -457,7 +547,7 @@ template <class Sys>
 int sys_host_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const double* z0, const double* lb, const double* ub,
                                   double* z, double* lam, double* zL, double* zU, double* obj, double* kkt_err, double* con_inf,
                                   int32_t* status, int32_t* iters, double* ws, size_t ws_doubles) {
-  return dispatch_scheme<Sys>(desc, B, [&](auto s, const Problem& P) {
+  return dispatch_any<Sys>(desc, B, [&](auto s, const Problem& P) {
     using S = decltype(s);
     const Layout<S> L(P);
     if (ws_doubles < (size_t)B * L.total) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)B * L.total);
@@ -466,7 +556,7 @@ int sys_host_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const
     std::vector<double> red(64), sig((size_t)L.Q * S::NW);
     std::vector<uint32_t> fix(L.Q);
     for (int b = 0; b < B; ++b)
-      ipm_solve_instance<S>(P, O, io, b, ws + (long long)b * L.total + L.crD, red.data(), sig.data(), fix.data());
+      ipm_solve_entry<S>(P, O, io, b, ws + (long long)b * L.total + L.crD, red.data(), sig.data(), fix.data());
     return (int)MYR_OK;
   });
 }

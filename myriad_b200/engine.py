@@ -46,6 +46,12 @@ class Engine:
     self.desc = desc
     self.sizes = ML.problem_sizes(desc)
     self._ws = None
+    s = self.sizes
+    if desc.optimizer == ML.OPT_SHOOTING:
+      # per interval: (n + 1) x (n + (mc*cpi + 1) m); row n = gradient of the interval's integrated cost
+      self.jblk_shape = (desc.intervals, s.n + 1, s.jac_block_doubles // (desc.intervals * (s.n + 1)))
+    else:
+      self.jblk_shape = (s.stages, s.stage_nodes, s.nc, s.nw)
 
   # ---- K1
   def eval(self, z: torch.Tensor, lam: Optional[torch.Tensor] = None, hessian: bool = False, out: Optional[EvalResult] = None) -> EvalResult:
@@ -59,7 +65,7 @@ class Engine:
         f=torch.empty(B, dtype=torch.float64, device=dev),
         grad=torch.empty(B, s.nvars, dtype=torch.float64, device=dev),
         c=torch.empty(B, s.ncon, dtype=torch.float64, device=dev),
-        Jblk=torch.empty(B, s.stages, s.stage_nodes, s.nc, s.nw, dtype=torch.float64, device=dev),
+        Jblk=torch.empty((B,) + self.jblk_shape, dtype=torch.float64, device=dev),
         Hblk=torch.empty(B, s.nodes, s.nw * (s.nw + 1) // 2, dtype=torch.float64, device=dev) if hessian else None)
     if hessian and lam is None:
       lam = torch.zeros(B, s.ncon, dtype=torch.float64, device=dev)

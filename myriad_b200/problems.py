@@ -182,6 +182,18 @@ def block_index_maps(tr: Transcription):
 def dense_jacobian(tr: Transcription, Jblk: torch.Tensor) -> torch.Tensor:
   """Compact block Jacobian [B, stages, stage_nodes, nc, nw] -> dense [B, ncon, nvars] (what jax.jacrev
   returns in the reference, myriad/nlp_solvers/__init__.py:37)."""
+  if tr.optimizer == SHOOTING:
+    # Jblk [B, K, n+1, ncol]: rows 0..n-1 = d px_k / d (xs[k], controls of interval k); d c_k / d xs[k+1] = -I
+    B, K, _, ncol = Jblk.shape
+    n, m = tr.n, tr.m
+    M = tr.mc * tr.cpi
+    out = torch.zeros(B, tr.ncon, tr.nvars, dtype=Jblk.dtype, device=Jblk.device)
+    ubase = (K + 1) * n
+    for k in range(K):
+      out[:, k * n:(k + 1) * n, k * n:(k + 1) * n] += Jblk[:, k, :n, :n]
+      out[:, k * n:(k + 1) * n, ubase + k * M * m: ubase + (k * M + M + 1) * m] += Jblk[:, k, :n, n:]
+      out[:, k * n:(k + 1) * n, (k + 1) * n:(k + 2) * n] -= torch.eye(n, dtype=Jblk.dtype, device=Jblk.device)
+    return out
   zidx, cidx, stage_node = block_index_maps(tr)
   B = Jblk.shape[0]
   S, sn, nc, nw = Jblk.shape[1:]

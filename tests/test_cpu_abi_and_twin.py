@@ -82,6 +82,20 @@ def _host_eval(ML, d, s, z, lam=None):
   return f, grad, c, J, H
 
 
+def _dense_J_shooting(s, J, K, cpi, meth):
+  n, m = s.n, s.m
+  M = (2 if meth == "RK4" else 1) * cpi
+  ncol = n + (M + 1) * m
+  Jb = J.reshape(K, n + 1, ncol)
+  Jd = np.zeros((s.ncon, s.nvars))
+  ubase = (K + 1) * n
+  for k in range(K):
+    Jd[k * n:(k + 1) * n, k * n:(k + 1) * n] += Jb[k, :n, :n]
+    Jd[k * n:(k + 1) * n, ubase + k * M * m: ubase + (k * M + M + 1) * m] += Jb[k, :n, n:]
+    Jd[k * n:(k + 1) * n, (k + 1) * n:(k + 2) * n] -= np.eye(n)
+  return Jd
+
+
 def _dense_J(s, J, quad):
   n, m, Q = s.n, s.m, s.nodes
   zidx = lambda q, i: q * n + i if i < n else Q * n + q * m + (i - n)
@@ -97,16 +111,19 @@ def _dense_J(s, J, quad):
   return Jd
 
 
-@pytest.mark.parametrize("case", COLLOC)
+@pytest.mark.parametrize("case", sorted(CASES))
 def test_host_twin_k1_matches_reference_fixture(ML, case):
+  """f, c, grad f and the (block) Jacobian of all three transcriptions x four integrators vs the reference's closures."""
   fx = load(case)
   d = _desc(ML, case)
   s = ML.problem_sizes(d)
+  sysname, opt, quad, meth, K, cpi = CASES[case]
   f, grad, c, J, _ = _host_eval(ML, d, s, np.ascontiguousarray(np.stack([fx["z"], fx["guess"]])))
   np.testing.assert_allclose(f, [fx["obj_z"], fx["obj_guess"]], rtol=1e-12, atol=1e-14)
   np.testing.assert_allclose(c, np.stack([fx["con_z"], fx["con_guess"]]), rtol=1e-12, atol=1e-13)
-  np.testing.assert_allclose(grad[0], fx["grad_z"], rtol=1e-12, atol=1e-13)
-  np.testing.assert_allclose(_dense_J(s, J[0], CASES[case][2]), fx["jac_z"], rtol=1e-12, atol=1e-13)
+  np.testing.assert_allclose(grad[0], fx["grad_z"], rtol=1e-11, atol=1e-13)
+  Jd = _dense_J_shooting(s, J[0], K, cpi, meth) if opt == "SHOOTING" else _dense_J(s, J[0], quad)
+  np.testing.assert_allclose(Jd, fx["jac_z"], rtol=1e-11, atol=1e-13)
 
 
 def _host_ipm(ML, d, s, z0, lb, ub, max_iter=1000):
@@ -120,7 +137,7 @@ def _host_ipm(ML, d, s, z0, lb, ub, max_iter=1000):
   return out
 
 
-@pytest.mark.parametrize("case", [c for c in COLLOC if "sol_cost" in load(c)])
+@pytest.mark.parametrize("case", [c for c in sorted(CASES) if "sol_cost" in load(c)])
 def test_host_twin_ipm_matches_reference_solve(ML, case):
   fx = load(case)
   d = _desc(ML, case)
@@ -129,7 +146,8 @@ def test_host_twin_ipm_matches_reference_solve(ML, case):
                   np.ascontiguousarray(fx["bounds"][None, :, 1]))
   assert out["status"][0] == 0 and out["cinf"][0] <= 1e-8
   ref = float(fx["sol_cost"])
-  assert abs(out["obj"][0] - ref) <= 1e-5 * max(1.0, abs(ref))
+  # SciPy's default ftol=1e-6 leaves SLSQP up to ~3e-5 short of the optimum on the flat SIMPLECASE objectives
+  assert abs(out["obj"][0] - ref) <= 5e-5 * max(1.0, abs(ref))
   assert out["obj"][0] <= ref + 1e-7 * max(1.0, abs(ref))
   # KKT conditions re-checked independently with the oracle's derivatives
   from oracle import nlp

@@ -15,7 +15,8 @@ from tests.cases import CASES, load
 pytestmark = pytest.mark.gpu
 
 COLLOC = sorted(c for c, v in CASES.items() if v[1] == "COLLOCATION")
-SOLVED = [c for c in COLLOC if "sol_cost" in load(c)]
+ALL = sorted(CASES)
+SOLVED = [c for c in ALL if "sol_cost" in load(c)]
 
 
 def _tr(case):
@@ -23,7 +24,7 @@ def _tr(case):
   from myriad_b200.systems import SystemType
   sysname, opt, quad, meth, intervals, cpi = CASES[case]
   system = SystemType[sysname]()
-  optid = PR.TRAPEZOIDAL if quad == "TRAPEZOIDAL" else PR.HERMITE_SIMPSON
+  optid = PR.SHOOTING if opt == "SHOOTING" else (PR.TRAPEZOIDAL if quad == "TRAPEZOIDAL" else PR.HERMITE_SIMPSON)
   return PR.Transcription(system, optid, meth, intervals, cpi)
 
 
@@ -36,7 +37,7 @@ def _dev(a):
   return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda().contiguous()
 
 
-@pytest.mark.parametrize("case", COLLOC)
+@pytest.mark.parametrize("case", ALL)
 def test_k1_matches_reference_fixture(case):
   from myriad_b200 import problems as PR
   fx = load(case)
@@ -131,7 +132,8 @@ def test_k3_solution_matches_reference_solve(case):
   assert float(out["con_inf"][0]) <= 1e-8
   obj = float(out["obj"][0])
   ref = float(fx["sol_cost"])
-  assert abs(obj - ref) <= 1e-5 * max(1.0, abs(ref)), (obj, ref)
+  # SciPy's default ftol=1e-6 leaves SLSQP up to ~3e-5 short of the optimum on the flat SIMPLECASE objectives
+  assert abs(obj - ref) <= 5e-5 * max(1.0, abs(ref)), (obj, ref)
   assert obj <= ref + 1e-7 * max(1.0, abs(ref))  # the IPM is converged tighter than SLSQP's ftol=1e-6
 
 
