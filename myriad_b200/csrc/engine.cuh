@@ -20,6 +20,9 @@ struct IpmOpts {
   double bound_push, bound_frac, bound_relax, kappa_sigma, s_max;
   double delta_min, delta_0, delta_max, delta_c, kappa_w_minus, kappa_w_plus, kappa_w_plus_first;
   double eta, rho;
+  double delta_reg;   // tiny primal regularisation of the node blocks, removed again by iterative refinement
+  int max_refine;
+  int reserved2;
 };
 
 enum Status : int { ST_SOLVED = 0, ST_ACCEPTABLE = 1, ST_MAXITER = -1, ST_LINESEARCH = -2, ST_INERTIA = -3, ST_NAN = -13 };
@@ -222,6 +225,8 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
       }
 #pragma unroll
       for (int r = 0; r < NC; ++r) b[i * NC + r] = vb[r];
+#pragma unroll
+      for (int k = 0; k < BB; ++k) D[i * BB + k] = Dinv[k];  // keep the pivot inverse for later re-solves
     }
     MYR_SYNC();
     // update even multiples of s
@@ -308,6 +313,8 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
       for (int k = 0; k < NC; ++k) a += Dinv[r * NC + k] * b[k];
       x[r] = a;
     }
+#pragma unroll
+    for (int k = 0; k < BB; ++k) D[k] = Dinv[k];
   }
   MYR_SYNC();
   // back substitution
@@ -347,6 +354,93 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
   MYR_SYNC();
 }
 
+// Re-solve with the factors left by block_cr_solve (pivot inverses in D, VL, VU) for a new right-hand side b
+// (destroyed); x receives the solution.  One barrier per level: since VL_e = Dinv_e U_{e-s}^T and VU_e = Dinv_e U_e,
+// the elimination of e from its surviving neighbours is  b_i -= VL_e^T b_e  (right neighbour e = i+s) and
+// b_i -= VU_e^T b_e (left neighbour e = i-s), which only needs data of already-final eliminated nodes.
+template <int NC>
+MYR_HDI void block_cr_resolve(int St, const double* D, const double* VL, const double* VU, double* b, double* x) {
+  constexpr int BB = NC * NC;
+  int s = 1;
+  for (; s < St; s <<= 1) {
+    for (int i = 2 * MYR_TID * s; i < St; i += 2 * MYR_NT * s) {
+      double bn[NC];
+#pragma unroll
+      for (int r = 0; r < NC; ++r) bn[r] = b[i * NC + r];
+      const int er = i + s, el = i - s;
+      if (er < St) {
+        const double* vl = VL + er * BB;
+#pragma unroll
+        for (int r = 0; r < NC; ++r) {
+          double a = 0.0;
+#pragma unroll
+          for (int k = 0; k < NC; ++k) a += vl[k * NC + r] * b[er * NC + k];
+          bn[r] -= a;
+        }
+      }
+      if (el >= 0) {
+        const double* vu = VU + el * BB;
+#pragma unroll
+        for (int r = 0; r < NC; ++r) {
+          double a = 0.0;
+#pragma unroll
+          for (int k = 0; k < NC; ++k) a += vu[k * NC + r] * b[el * NC + k];
+          bn[r] -= a;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NC; ++r) b[i * NC + r] = bn[r];
+    }
+    MYR_SYNC();
+  }
+  if (MYR_TID == 0) {
+#pragma unroll
+    for (int r = 0; r < NC; ++r) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) a += D[r * NC + k] * b[k];
+      x[r] = a;
+    }
+  }
+  MYR_SYNC();
+  for (s >>= 1; s >= 1; s >>= 1) {
+    for (int i = (2 * MYR_TID + 1) * s; i < St; i += 2 * MYR_NT * s) {
+      double xi[NC];
+      const double* di = D + i * BB;
+#pragma unroll
+      for (int r = 0; r < NC; ++r) {
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) a += di[r * NC + k] * b[i * NC + k];
+        xi[r] = a;
+      }
+      const double* vl = VL + i * BB;
+      const double* xl = x + (i - s) * NC;
+#pragma unroll
+      for (int r = 0; r < NC; ++r) {
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) a += vl[r * NC + k] * xl[k];
+        xi[r] -= a;
+      }
+      if (i + s < St) {
+        const double* vu = VU + i * BB;
+        const double* xr = x + (i + s) * NC;
+#pragma unroll
+        for (int r = 0; r < NC; ++r) {
+          double a = 0.0;
+#pragma unroll
+          for (int k = 0; k < NC; ++k) a += vu[r * NC + k] * xr[k];
+          xi[r] -= a;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NC; ++r) x[i * NC + r] = xi[r];
+    }
+    MYR_SYNC();
+  }
+}
+
 // KKT solve for one instance:
 //   [ H + Sigma + dw I   J^T ] [dz  ]     [ rb ]
 //   [ J               -dc I ] [dlam] = - [ c  ]
@@ -354,7 +448,8 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
 // Returns inertia-ok flag; dz (node-major) and dlam (stage-major) in the workspace.
 template <class S>
 MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const double* sigma /*node-major*/,
-                       const uint32_t* fixmask /*per node*/, double delta_w, double delta_c, double* cr, double* red) {
+                       const uint32_t* fixmask /*per node*/, double delta_w, double delta_c, double* cr, double* red,
+                       double delta_reg = 0.0, int max_refine = 0) {
   constexpr int NW = S::NW, NC = S::NC;
   const int Q = L.Q, St = L.St;
   // ---- node blocks: Hinv = (W + Sigma + dw)^-1 with fixed variables removed; inertia of H
@@ -367,7 +462,7 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
 #pragma unroll
       for (int j = 0; j < NW; ++j) A[i * NW + j] = Wq[pidx(i, j, NW)];
 #pragma unroll
-    for (int i = 0; i < NW; ++i) A[i * NW + i] += sigma[q * NW + i] + delta_w;
+    for (int i = 0; i < NW; ++i) A[i * NW + i] += sigma[q * NW + i] + delta_w + delta_reg;
     int p_, n_, z_;
     sym_inverse<NW>(A, fixmask[q], inv, p_, n_, z_);
     hp += p_; hn += n_; hz += z_;
@@ -467,6 +562,127 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
     }
   }
   MYR_SYNC();
+  // ---- iterative refinement against the matrix WITHOUT delta_reg: the node blocks are factorised with a tiny
+  // regularisation (directions in which W + Sigma is singular, e.g. a state that enters neither cost nor dynamics and is
+  // far from its bounds, would otherwise make the block elimination break down although the KKT matrix is regular);
+  // the refinement removes its effect and recovers the digits the Schur complement loses.
+  for (int itr = 0; ok && itr < max_refine; ++itr) {
+    // node residual  rz = -rb - (H dz + G^T dlam_phi + F^T dlam_psi)   (stored in dzL), norms
+    double rmax = 0.0, smax = 0.0;
+    for (int q = MYR_TID; q < Q; q += MYR_NT) {
+      double v[NW], d[NW];
+#pragma unroll
+      for (int i = 0; i < NW; ++i) { v[i] = -w[L.rb + q * NW + i]; d[i] = w[L.dz + q * NW + i]; smax = fmax(smax, fabs(v[i])); }
+      const double* Wq = w + L.W + q * S::NWP;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) {
+        double a = (sigma[q * NW + i] + delta_w) * d[i];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) a += Wq[pidx(i, k, NW)] * d[k];
+        v[i] -= a;
+      }
+      const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
+      if (jp >= 0) {
+        const double* Gq = w + L.G + q * NC * NW;
+#pragma unroll
+        for (int r = 0; r < NC; ++r) {
+          const double dl = w[L.dlam + jp * NC + r];
+#pragma unroll
+          for (int i = 0; i < NW; ++i) v[i] -= Gq[r * NW + i] * dl;
+        }
+      }
+      if (js >= 0) {
+        const double* Fq = w + L.F + q * NC * NW;
+#pragma unroll
+        for (int r = 0; r < NC; ++r) {
+          const double dl = w[L.dlam + js * NC + r];
+#pragma unroll
+          for (int i = 0; i < NW; ++i) v[i] -= Fq[r * NW + i] * dl;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NW; ++i) {
+        const bool fx = (fixmask[q] >> i) & 1u;
+        const double r_ = fx ? 0.0 : v[i];
+        w[L.dzL + q * NW + i] = r_;
+        rmax = fmax(rmax, (r_ != r_) ? INFINITY : fabs(r_));
+      }
+    }
+    MYR_SYNC();
+    // stage residual rc = -c - (J dz - dc dlam), and the Schur right-hand side  J Hinv rz - rc
+    for (int j = MYR_TID; j < St; j += MYR_NT) {
+      double rc[NC], bj[NC];
+#pragma unroll
+      for (int r = 0; r < NC; ++r) { rc[r] = -w[L.c + j * NC + r] + delta_c * w[L.dlam + j * NC + r]; bj[r] = 0.0; smax = fmax(smax, fabs(w[L.c + j * NC + r])); }
+      const int nk = S::stage_nodes(P, j);
+      for (int k = 0; k < nk; ++k) {
+        int role; const int q = S::stage_node(P, j, k, role);
+        const double* Jq = w + (role ? L.F : L.G) + q * NC * NW;
+        const double* Hi = w + L.Hinv + q * NW * NW;
+        double t[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          double a = 0.0;
+#pragma unroll
+          for (int k2 = 0; k2 < NW; ++k2) a += Hi[i * NW + k2] * w[L.dzL + q * NW + k2];
+          t[i] = a;
+        }
+#pragma unroll
+        for (int r = 0; r < NC; ++r) {
+          double a = 0.0, b_ = 0.0;
+#pragma unroll
+          for (int i = 0; i < NW; ++i) { a += Jq[r * NW + i] * w[L.dz + q * NW + i]; b_ += Jq[r * NW + i] * t[i]; }
+          rc[r] -= a; bj[r] += b_;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NC; ++r) {
+        rmax = fmax(rmax, (rc[r] != rc[r]) ? INFINITY : fabs(rc[r]));
+        bb[j * NC + r] = bj[r] - rc[r];
+      }
+    }
+    rmax = block_max(rmax, red);
+    smax = block_max(smax, red);
+    MYR_SYNC();
+    if (!(rmax > 1e-13 * fmax(1.0, smax)) || !isfinite(rmax)) break;
+    block_cr_resolve<NC>(St, D, VL, VU, bb, w + L.dzU /* ddlam: St*NC <= Q*NW */);
+    for (int j = MYR_TID; j < St; j += MYR_NT)
+#pragma unroll
+      for (int r = 0; r < NC; ++r) w[L.dlam + j * NC + r] += w[L.dzU + j * NC + r];
+    for (int q = MYR_TID; q < Q; q += MYR_NT) {
+      double v[NW];
+#pragma unroll
+      for (int i = 0; i < NW; ++i) v[i] = w[L.dzL + q * NW + i];
+      const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
+      if (jp >= 0) {
+        const double* Gq = w + L.G + q * NC * NW;
+#pragma unroll
+        for (int r = 0; r < NC; ++r) {
+          const double d = w[L.dzU + jp * NC + r];
+#pragma unroll
+          for (int i = 0; i < NW; ++i) v[i] -= Gq[r * NW + i] * d;
+        }
+      }
+      if (js >= 0) {
+        const double* Fq = w + L.F + q * NC * NW;
+#pragma unroll
+        for (int r = 0; r < NC; ++r) {
+          const double d = w[L.dzU + js * NC + r];
+#pragma unroll
+          for (int i = 0; i < NW; ++i) v[i] -= Fq[r * NW + i] * d;
+        }
+      }
+      const double* Hi = w + L.Hinv + q * NW * NW;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) a += Hi[i * NW + k] * v[k];
+        w[L.dz + q * NW + i] += a;
+      }
+    }
+    MYR_SYNC();
+  }
   return ok;
 }
 
@@ -606,7 +822,7 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     const double sc = nbnd > 0 ? fmax(O.s_max, sumz / nbnd) / O.s_max : 1.0;
     // lifted shooting: step defects accumulate along an interval's rollout, so the per-step feasibility tolerance is
     // tightened by cpi to keep the REFERENCE constraint px_k - x_{k+1} within tol
-    const double cscale = scheme_is_lifted<S>::value ? (double)P.cpi : 1.0;
+    const double cscale = scheme_is_lifted<S>::value ? 10.0 * (double)P.cpi : 1.0;
     auto Emu = [&](double m_) {
       const double comp = nbnd > 0 ? fmax(szmax - m_, m_ - szmin) / sc : 0.0;
       return fmax(fmax(rdmax / sd, cinf * cscale), comp);
@@ -640,7 +856,7 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     double delta = 0.0;
     bool ok = false;
     for (int tries = 0; tries < 60; ++tries) {
-      ok = kkt_solve<S>(P, L, w, sig_sh, fix_sh, delta, O.delta_c, cr, red);
+      ok = kkt_solve<S>(P, L, w, sig_sh, fix_sh, delta, O.delta_c, cr, red, O.delta_reg, O.max_refine);
       if (ok) break;
       if (delta == 0.0) delta = (delta_last == 0.0) ? O.delta_0 : fmax(O.delta_min, O.kappa_w_minus * delta_last);
       else delta *= (delta_last == 0.0) ? O.kappa_w_plus_first : O.kappa_w_plus;
@@ -738,10 +954,11 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       stage_constraints<S>(P, L, w, w + L.crb /*scratch*/, red, ci_t, c1_t);
       blog = block_sum(blog, red);
       const double phit = f_t - mu * blog + nu * c1_t;
-      if (isfinite(phit) && phit <= phi0 + O.eta * alpha * Dm) { accepted = true; break; }
+      // Armijo with IPOPT's rounding-error relaxation (10 eps |phi|) so that converged iterates are not rejected by cancellation
+      if (isfinite(phit) && phit <= phi0 + O.eta * alpha * Dm + 10.0 * 2.220446049250313e-16 * fabs(phi0)) { accepted = true; break; }
       alpha *= 0.5;
     }
-    if (!accepted) { status = ST_LINESEARCH; break; }
+    if (!accepted) { status = (E0 <= O.acceptable_tol) ? ST_ACCEPTABLE : ST_LINESEARCH; break; }
 
     // ---------------- accept: primal, equality multipliers, bound multipliers (with the kappa_sigma safeguard)
     for (int q = MYR_TID; q < Q; q += MYR_NT) {

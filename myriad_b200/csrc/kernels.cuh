@@ -505,6 +505,7 @@ inline IpmOpts make_opts(const MyrIpmOpts* o) {
   r.delta_min = 1e-20; r.delta_0 = 1e-4; r.delta_max = 1e40; r.delta_c = 0.0;
   r.kappa_w_minus = 1.0 / 3.0; r.kappa_w_plus = 8.0; r.kappa_w_plus_first = 100.0;
   r.eta = 1e-4; r.rho = 0.1;
+  r.delta_reg = 1e-8; r.max_refine = 3;
   return r;
 }
 
