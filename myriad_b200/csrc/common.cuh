@@ -213,7 +213,7 @@ __host__ __device__ __noinline__ void sym_inverse_inertia(double* A, uint32_t ma
 // back to the pivoted Bunch-Parlett routine above.  Masked (fixed) variables are decoupled before factorising
 // and their rows/cols of the inverse are zero.  A: full symmetric N x N (not modified).
 template <int N>
-MYR_HDI bool sym_inverse_inertia_fast(const double* A, uint32_t mask, double* inv, int& npos, int& nneg) {
+MYR_HDI bool sym_inverse_inertia_fast(const double* A, uint32_t mask, double* inv, int& npos, int& nneg, double& piv_ratio) {
   double a[N][N];
   double scale = 0.0;
 #pragma unroll
@@ -229,6 +229,7 @@ MYR_HDI bool sym_inverse_inertia_fast(const double* A, uint32_t mask, double* in
   double d[N], l[N][N];
   bool ok = true;
   int np_ = 0, nn_ = 0;
+  double minpiv = INFINITY;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     double dk = a[k][k];
@@ -236,6 +237,7 @@ MYR_HDI bool sym_inverse_inertia_fast(const double* A, uint32_t mask, double* in
     for (int j = 0; j < k; ++j) dk -= l[k][j] * l[k][j] * d[j];
     d[k] = dk;
     ok = ok && (fabs(dk) > thresh);
+    minpiv = fmin(minpiv, fabs(dk));
     const bool masked = (mask >> k) & 1u;
     if (!masked) { if (dk > 0) ++np_; else ++nn_; }
     const double rk = 1.0 / dk;
@@ -282,14 +284,17 @@ MYR_HDI bool sym_inverse_inertia_fast(const double* A, uint32_t mask, double* in
       inv[j * N + i] = v;
     }
   npos = np_; nneg = nn_;
+  piv_ratio = minpiv / fmax(scale, 1e-300);
   return true;
 }
 
 // inverse + inertia: fast path first, pivoted fallback
 template <int N>
-MYR_HDI void sym_inverse(double* A, uint32_t mask, double* inv, int& npos, int& nneg, int& nzero) {
+MYR_HDI void sym_inverse(double* A, uint32_t mask, double* inv, int& npos, int& nneg, int& nzero, double* piv_ratio = nullptr) {
   nzero = 0;
-  if (sym_inverse_inertia_fast<N>(A, mask, inv, npos, nneg)) return;
+  double pr = 0.0;
+  if (sym_inverse_inertia_fast<N>(A, mask, inv, npos, nneg, pr)) { if (piv_ratio) *piv_ratio = pr; return; }
+  if (piv_ratio) *piv_ratio = 0.0;  // pivoted fallback: treat as ill-conditioned
   sym_inverse_inertia<N>(A, mask, inv, npos, nneg, nzero);
 }
 

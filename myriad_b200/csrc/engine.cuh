@@ -454,6 +454,7 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
   const int Q = L.Q, St = L.St;
   // ---- node blocks: Hinv = (W + Sigma + dw)^-1 with fixed variables removed; inertia of H
   int hp = 0, hn = 0, hz = 0;
+  double minpr = INFINITY;
   for (int q = MYR_TID; q < Q; q += MYR_NT) {
     double A[NW * NW], inv[NW * NW];
     const double* Wq = w + L.W + q * S::NWP;
@@ -464,13 +465,18 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
 #pragma unroll
     for (int i = 0; i < NW; ++i) A[i * NW + i] += sigma[q * NW + i] + delta_w + delta_reg;
     int p_, n_, z_;
-    sym_inverse<NW>(A, fixmask[q], inv, p_, n_, z_);
+    double pr_;
+    sym_inverse<NW>(A, fixmask[q], inv, p_, n_, z_, &pr_);
+    minpr = fmin(minpr, pr_);
     hp += p_; hn += n_; hz += z_;
 #pragma unroll
     for (int i = 0; i < NW * NW; ++i) w[L.Hinv + q * NW * NW + i] = inv[i];
   }
   const int Hneg = (int)(block_sum((double)hn, red) + 0.5);
   const int Hzero = (int)(block_sum((double)hz, red) + 0.5);
+  minpr = block_min(minpr, red);
+  // refinement is only worth its cost when some node block was close to singular
+  if (!(minpr < 1e-4)) max_refine = 0;
   (void)hp;
   MYR_SYNC();
   // ---- stage blocks of the Schur complement S = J Hinv J^T + dc I and its right-hand side  c - J Hinv rb
@@ -823,11 +829,11 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     // lifted shooting: step defects accumulate along an interval's rollout, so the per-step feasibility tolerance is
     // tightened by cpi to keep the REFERENCE constraint px_k - x_{k+1} within tol
     const double cscale = scheme_is_lifted<S>::value ? 10.0 * (double)P.cpi : 1.0;
-    auto Emu = [&](double m_) {
+    auto Emu = [&](double m_, double cs = 1.0) {
       const double comp = nbnd > 0 ? fmax(szmax - m_, m_ - szmin) / sc : 0.0;
-      return fmax(fmax(rdmax / sd, cinf * cscale), comp);
+      return fmax(fmax(rdmax / sd, cinf * cs), comp);
     };
-    E0 = Emu(0.0);
+    E0 = Emu(0.0, cscale);  // the tightening applies to termination only, not to the barrier-parameter schedule
     if (!(E0 == E0) || !isfinite(f)) { status = ST_NAN; break; }
     if (E0 <= O.tol) { status = ST_SOLVED; break; }
     if (E0 <= O.acceptable_tol) { if (++n_acceptable >= O.acceptable_iter) { status = ST_ACCEPTABLE; break; } } else n_acceptable = 0;
@@ -856,7 +862,8 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     double delta = 0.0;
     bool ok = false;
     for (int tries = 0; tries < 60; ++tries) {
-      ok = kkt_solve<S>(P, L, w, sig_sh, fix_sh, delta, O.delta_c, cr, red, O.delta_reg, O.max_refine);
+      // accurate steps only matter near the solution: refine the linear solve in the end game only
+      ok = kkt_solve<S>(P, L, w, sig_sh, fix_sh, delta, O.delta_c, cr, red, O.delta_reg, E0 < 1e-3 ? O.max_refine : 0);
       if (ok) break;
       if (delta == 0.0) delta = (delta_last == 0.0) ? O.delta_0 : fmax(O.delta_min, O.kappa_w_minus * delta_last);
       else delta *= (delta_last == 0.0) ? O.kappa_w_plus_first : O.kappa_w_plus;

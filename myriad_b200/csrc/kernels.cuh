@@ -2,6 +2,7 @@
 // parallelises; api.cu dispatches through the per-system tables.
 #pragma once
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -505,7 +506,9 @@ inline IpmOpts make_opts(const MyrIpmOpts* o) {
   r.delta_min = 1e-20; r.delta_0 = 1e-4; r.delta_max = 1e40; r.delta_c = 0.0;
   r.kappa_w_minus = 1.0 / 3.0; r.kappa_w_plus = 8.0; r.kappa_w_plus_first = 100.0;
   r.eta = 1e-4; r.rho = 0.1;
-  r.delta_reg = 1e-8; r.max_refine = 3;
+  r.delta_reg = 1e-8; r.max_refine = 1;
+  if (const char* e = getenv("MYR_DELTA_REG")) r.delta_reg = atof(e);      // tuning knobs (debug)
+  if (const char* e = getenv("MYR_MAX_REFINE")) r.max_refine = atoi(e);
   return r;
 }
 
