@@ -12,8 +12,8 @@ collective); one NCCL all_gather of the packed solutions closes each step.
 Printed JSON (rank 0, one line) follows the contract in the task statement: value = device-timed whole-job
 solves/s with inputs resident in HBM; e2e = same metric through the public Python API from pinned HOST buffers
 (H2D of the start states, problem construction, solve, rollout, D2H of the results inside the timed region);
-roofline = the rollout+Jacobian kernel K1 (myr_eval) timed live with CUDA events and an L2 flush before each
-launch; cpu_baseline = the CPU oracle (reference algorithm restated, SciPy SLSQP) on a bounded sample.
+roofline = the rollout+Jacobian kernel K1 (myr_eval) timed live with CUDA events over a working set larger than L2
+(back-to-back launches); roofline_ipm = the interior-point kernel's algorithmic fp64 FLOP/s against a live DFMA peak; cpu_baseline = the CPU oracle (reference algorithm restated, SciPy SLSQP) on a bounded sample.
 """
 from __future__ import annotations
 
@@ -35,7 +35,7 @@ METRIC = "trajopt solves/sec (CARTPOLE collocation N=100, batched)"
 def parse():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--steps", type=int, default=40)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--batch", type=int, default=1024, help="instances per GPU per step")
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -105,7 +105,7 @@ class ClockSampler:
             self.reasons.add(nme)
       except Exception:
         pass
-      self._stop.wait(0.2)
+      self._stop.wait(0.05)
 
   def __enter__(self):
     self._t.start()
@@ -118,6 +118,25 @@ class ClockSampler:
   def summary(self):
     s = sorted(self.samples)
     return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one eval_kernel launch at B=8192 (ncu --set full, round 1)
+K1_NCU_TRAFFIC_BYTES = 295.45e6
+
+
+def ipm_flops_per_iteration(sz) -> dict:
+  """Algorithmic fp64 flops of one interior-point iteration of one instance: node evaluation with
+  Hessian, one KKT solve (node-block LDL^T inverses, Schur complement, block cyclic reduction, back-substitution) and
+  one values-only line-search evaluation, for Q nodes of NW variables and St stages of NC rows, k nodes per stage."""
+  Q, St, NW, NC, k = sz.nodes, sz.stages, sz.nw, sz.nc, sz.stage_nodes
+  node_inv = Q * 2 * NW ** 3
+  schur = St * (k * (2 * NC * NW * NW + 2 * NC * NC * NW + 2 * NC * NW) + 2 * NC * NC * NW)
+  cr = St * (2 * NC ** 3 + 2 * 2 * NC ** 3 + 2 * NC * NC + 2 * (2 * 2 * NC ** 3 + 2 * NC * NC) + 2 * 2 * NC * NC)
+  dz = Q * (2 * 2 * NC * NW + 2 * NW * NW)
+  k1 = Q * 400 + Q * 100  # generated f/J/Hessian code of CARTPOLE (~400 flops incl. sincos) + values-only trial evaluation
+  vec = 30 * Q * NW      # residuals, barrier terms, fraction-to-boundary, updates
+  return {"node_inverse": node_inv, "schur": schur, "block_cr": cr, "dz": dz, "k1": k1, "vector": vec,
+          "total": node_inv + schur + cr + dz + k1 + vec}
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -218,9 +237,9 @@ def b200_arm(args):
     return float(t[0]), wall
 
   warm = max(args.warmup, 3)
-  with ClockSampler(local) as clk:
+  with ClockSampler(local) as clk:  # clocks are sampled during both timed regions (device-resident and end-to-end)
     ms_dev, wall_dev = timed(device_step, args.steps, warm)
-  ms_e2e, _ = timed(e2e_step, args.steps, warm)
+    ms_e2e, _ = timed(e2e_step, args.steps, warm)
   h2d, d2h = e2e_step()
 
   status = out["status"]
@@ -233,8 +252,8 @@ def b200_arm(args):
     n_ok_all = n_ok
   iters = out["iters"].double()
 
-  # ---- roofline of K1 (rollout + defect + block Jacobian kernel), timed live, L2 flushed before every launch
-  roof = None
+  # ---- roofline of K1 (rollout + defect + block Jacobian kernel), timed live over a working set larger than L2
+  roof = roof_ipm = None
   if rank == 0:
     peaks = {}
     try:
@@ -242,24 +261,61 @@ def b200_arm(args):
     except Exception:
       pass
     peak, which = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-    Bk = max(B, 8192)  # working set must exceed the 126 MB L2: 43 KB/instance -> >= 355 MB at 8192
+    Bk = max(B, 8192)  # working set must exceed the 126 MB L2: 43 KB/instance -> >= 355 MB at 8192 (no flush needed)
     zk = out["z"][:1].expand(Bk, -1).contiguous() + 0.01 * torch.randn(Bk, sz.nvars, dtype=torch.float64, device=dev)
     r = eng.eval(zk)
+    for _ in range(3):
+      eng.eval(zk, out=r)
     torch.cuda.synchronize()
-    ts = []
-    for _ in range(10):
-      flush.fill_(0.0)
-      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      a.record(); eng.eval(zk, out=r); b.record()
-      torch.cuda.synchronize()
-      ts.append(a.elapsed_time(b))
-    t_k1 = sum(ts) / len(ts)
+    nrep = 20
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(nrep):
+      eng.eval(zk, out=r)
+    b.record()
+    torch.cuda.synchronize()
+    t_k1 = a.elapsed_time(b) / nrep
     alg_bytes = Bk * 8 * (sz.nvars + sz.ncon + sz.jac_block_doubles + sz.nvars + 1)  # read z; write c, Jblk, grad, f
     ach = alg_bytes / (t_k1 * 1e-3) / 1e9
     roof = {"kernel": "eval_kernel (K1: rollout + defects + block Jacobian)", "bound": "hbm", "achieved": ach, "peak": peak,
-            "unit": "GB/s", "frac": ach / peak, "peak_source": which, "traffic": None, "batch": Bk,
+            "unit": "GB/s", "frac": ach / peak, "peak_source": which, "traffic": K1_NCU_TRAFFIC_BYTES, "batch": Bk,
             "bytes_per_instance": alg_bytes // Bk, "us_per_launch": t_k1 * 1e3,
-            "note": "K1 is launched stand-alone here; inside the timed step it is fused into ipm_kernel (see DESIGN.md)"}
+            "l2": f"{nrep} back-to-back launches over a {alg_bytes / 1e6:.0f} MB working set (> 126 MB L2), no flush",
+            "traffic_source": "profiles/r1_k1_eval_trap_B8192_ncu_full.txt (dram read+write per launch at B=8192; part of the "
+                              "written lines is still dirty in L2 when the launch ends)",
+            "note": "K1 is launched stand-alone here (myr_eval); inside the timed step the same node evaluation runs fused "
+                    "inside ipm_kernel, whose own roofline is 'roofline_ipm'"}
+
+    # ---- fp64 peak (DFMA loop) and the interior-point kernel's algorithmic FLOP/s
+    import ctypes as C
+    from myriad_b200 import _lib as ML
+    scratch = torch.empty(148 * 8 * 1024, dtype=torch.float64, device=dev)
+    it_d = 20000
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ML.check(ML.lib().myr_bench_dfma(148 * 8, 1000, C.c_void_p(scratch.data_ptr()), st))
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record(); ML.check(ML.lib().myr_bench_dfma(148 * 8, it_d, C.c_void_p(scratch.data_ptr()), st)); b.record()
+      torch.cuda.synchronize()
+      best = min(best, a.elapsed_time(b))
+    fp64_peak = 2.0 * 8 * it_d * 1024 * 148 * 8 / (best * 1e-3) / 1e12
+    fl = ipm_flops_per_iteration(sz)
+    tot_iters = float(out["iters"].double().sum())
+    # time of the ipm kernel alone (no rollout / pack): CUDA events around one more solve
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); eng.ipm_solve(z0, lb, ub, max_iter=hp.max_iter, out=out); b.record()
+    torch.cuda.synchronize()
+    t_ipm = a.elapsed_time(b)
+    ach_f = fl["total"] * tot_iters / (t_ipm * 1e-3) / 1e12
+    roof_ipm = {"kernel": "ipm_kernel (K3 loop: K1 node evaluation + K2 block-CR KKT solve + line search), 98% of the step",
+                "bound": "fp64 latency/occupancy (neither hbm nor tensor: see DESIGN.md section 6)", "achieved": ach_f,
+                "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_f / fp64_peak,
+                "peak_source": "measured live: DFMA loop, 8 independent chains/thread, 148x8 CTAs x 1024 threads",
+                "flops_per_iteration": fl, "iterations_total": tot_iters, "ms_per_launch": t_ipm,
+                "note": "algorithmic flops (one KKT solve per iteration; inertia-correction retries and line-search "
+                        "re-evaluations beyond the first are not counted)"}
 
   cpu = None
   if rank == 0 and not args.no_cpu_baseline:
@@ -293,6 +349,7 @@ def b200_arm(args):
       "gpu_launches": 2 * args.steps,
       "clocks": clk.summary(),
       "roofline": roof,
+      "roofline_ipm": roof_ipm,
       "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -151,6 +151,11 @@ int myr_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B,
 int myr_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double* u, const double* x0,
                      double* xs, double* cost, void* stream);
 
+/* Measurement helper (no reference counterpart): launches `blocks` CTAs x 1024 threads, each doing `iters` rounds of 8
+ * independent fp64 FMAs (2 * 8 * iters * 1024 * blocks flops); out: [blocks * 1024] doubles.  bench.py times it with
+ * CUDA events to get the device's fp64 FMA peak, the denominator for the KKT / interior-point kernel's FLOP/s. */
+int myr_bench_dfma(int blocks, int iters, double* out, void* stream);
+
 /* Host twins (debug / CI only; HOST pointers; single-threaded). */
 int myr_host_eval(const MyrDesc* desc, int B, const double* z, const double* lam,
                   double* f, double* grad, double* c, double* Jblk, double* Hblk);

@@ -52,7 +52,7 @@ _P = C.c_void_p
 _lib = None
 
 EXPORTS = ["myr_abi_version", "myr_last_error", "myr_problem_sizes", "myr_eval", "myr_kkt_solve", "myr_ipm_solve",
-           "myr_rollout_cost", "myr_host_eval", "myr_host_kkt_solve", "myr_host_ipm_solve", "myr_host_rollout_cost"]
+           "myr_rollout_cost", "myr_bench_dfma", "myr_host_eval", "myr_host_kkt_solve", "myr_host_ipm_solve", "myr_host_rollout_cost"]
 
 
 def lib() -> C.CDLL:
@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
   ro = [C.POINTER(MyrDesc), C.c_int, C.c_int, _P, _P, _P, _P]
   L.myr_rollout_cost.argtypes = ro + [_P]
   L.myr_host_rollout_cost.argtypes = ro
+  L.myr_bench_dfma.argtypes = [C.c_int, C.c_int, _P, _P]
   for name in EXPORTS:
     if name not in ("myr_abi_version", "myr_last_error"):
       getattr(L, name).restype = C.c_int

@@ -41,11 +41,12 @@ def generated_systems():
   return out
 
 
-def _newest_source() -> float:
+def _newest_source(exclude=()) -> float:
   t = 0.0
   for d in (CSRC, os.path.join(ROOT, "include")):
     for f in os.listdir(d):
-      t = max(t, os.path.getmtime(os.path.join(d, f)))
+      if f not in exclude:
+        t = max(t, os.path.getmtime(os.path.join(d, f)))
   return t
 
 
@@ -65,6 +66,7 @@ def build(force: bool = False, systems=None, jobs: int | None = None, verbose: b
     if s not in gen:
       raise KeyError(f"system {s} has no generated device code (tools/gen_systems.py)")
   src_t = _newest_source()
+  sys_src_t = _newest_source(exclude=("api.cu",))  # the per-system units do not include the dispatcher
   tag = "_".join(sorted(names))
   stamp = os.path.join(BUILD, "systems.txt")
   prev = open(stamp).read() if os.path.exists(stamp) else ""
@@ -76,7 +78,7 @@ def build(force: bool = False, systems=None, jobs: int | None = None, verbose: b
   for s in names:
     obj = os.path.join(BUILD, f"sys_{s}.o")
     objs.append(obj)
-    if force or not os.path.exists(obj) or os.path.getmtime(obj) < src_t:
+    if force or not os.path.exists(obj) or os.path.getmtime(obj) < sys_src_t:
       tasks.append((s, [nvcc, *flags, f"-DMYR_SYS_CLASS={gen[s]}", "-c", os.path.join(CSRC, "sys_unit.cu"), "-o", obj]))
   api_obj = os.path.join(BUILD, "api.o")
   objs.append(api_obj)

@@ -108,3 +108,24 @@ extern "C" int myr_host_rollout_cost(const MyrDesc* desc, int B, int nu_rows, co
   MYR_GET(desc);
   return vt->host_rollout(desc, B, nu_rows, u, x0, xs, cost);
 }
+
+// ------------------------------------------------------------------ measurement helper
+// fp64 FMA peak of the device: 8 independent dependent-chains per thread, 1024 threads x `blocks` CTAs, `iters` rounds of
+// 8 FMAs.  2 * 8 * iters * threads flops.  Used by bench.py as the denominator of the KKT/IPM kernel's FLOP/s
+// (MEASURED_PEAKS.json has no fp64 figure).  out[blockIdx*blockDim + tid] receives a value so nothing is optimised away.
+__global__ void __launch_bounds__(1024) dfma_peak_kernel(int iters, double* out) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+extern "C" int myr_bench_dfma(int blocks, int iters, double* out, void* stream) {
+  if (blocks < 1 || iters < 1 || !out) return fail(MYR_E_BADARG, "bad arguments to myr_bench_dfma%s", "", 0);
+  dfma_peak_kernel<<<blocks, 1024, 0, (cudaStream_t)stream>>>(iters, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MYR_E_CUDA, "myr_bench_dfma: %s", cudaGetErrorString(e), 0);
+  return MYR_OK;
+}
