@@ -29,8 +29,10 @@
 extern "C" {
 #endif
 
-#define MYR_ABI_VERSION 1
+#define MYR_ABI_VERSION 2
 #define MYR_MAX_PARAMS 16
+#define MYR_MAX_NODE_LAYERS 5   /* Linear layers of a NODE MLP: up to 4 hidden + the output layer */
+#define MYR_MAX_NODE_WIDTH 128  /* widest hidden layer */
 
 /* SystemType members with a device implementation (myriad/systems/__init__.py:29-50). */
 enum {
@@ -43,7 +45,11 @@ enum {
   MYR_SYS_SIMPLECASEWITHBOUNDS = 6,
   MYR_SYS_GLUCOSE = 7,
   MYR_SYS_HARVEST = 8,
-  MYR_SYS_TIMBERHARVEST = 9
+  MYR_SYS_TIMBERHARVEST = 9,
+  /* NodeSystem (myriad/systems/neural_ode/node_system.py:14-42) wrapping true system k: id = MYR_SYS_NODE_BASE + k.
+   * Dynamics = the NODE MLP of myriad/neural_ode/create_node.py:110-117 (weights in MyrDesc.theta); cost, bounds,
+   * horizon and the verification rollout are the true system's. */
+  MYR_SYS_NODE_BASE = 100
 };
 /* OptimizerType x QuadratureRule (myriad/config.py:12-17,53-56; get_optimizer, trajectory_optimizers/__init__.py:12-28) */
 enum { MYR_OPT_SHOOTING = 0, MYR_OPT_TRAPEZOIDAL = 1, MYR_OPT_HERMITE_SIMPSON = 2 };
@@ -81,6 +87,15 @@ typedef struct MyrDesc {
   int32_t reserved;
   double T;                    /* horizon; <= 0 => system default */
   double params[MYR_MAX_PARAMS];
+  /* NODE systems only (system_id >= MYR_SYS_NODE_BASE), else zero.  The MLP is  Linear(h_1) sigmoid ... Linear(h_k)
+   * sigmoid Linear(n)  applied to concat(x, u) (create_node.py:110-117; hp.hidden_layers = node_hidden[0..k-1]).
+   * theta: DEVICE pointer for the device entry points (HOST pointer for myr_host_*), caller-owned, layer after layer
+   * in haiku's order (linear, linear_1, ...: create_node.py:124-131): w as (in, out) row-major -- hk.Linear computes
+   * x @ w + b -- followed by b (out). */
+  int32_t node_num_hidden;     /* k, 1..MYR_MAX_NODE_LAYERS-1 */
+  int32_t node_hidden[MYR_MAX_NODE_LAYERS - 1];
+  const double* theta;
+  int64_t theta_doubles;       /* length of theta, checked against the layer sizes */
 } MyrDesc;
 
 typedef struct MyrSizes {

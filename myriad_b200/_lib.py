@@ -12,6 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmyriad_b200.so")
 
 MAX_PARAMS = 16
+MAX_NODE_LAYERS = 5
+NODE_BASE = 100
 
 SYSTEM_IDS = {
   "SIMPLECASE": 0, "CARTPOLE": 1, "VANDERPOL": 2, "CANCERTREATMENT": 3, "MOULDFUNGICIDE": 4, "BIOREACTOR": 5,
@@ -28,7 +30,9 @@ class MyrDesc(C.Structure):
   _fields_ = [("system_id", C.c_int32), ("optimizer", C.c_int32), ("integration_method", C.c_int32),
               ("intervals", C.c_int32), ("controls_per_interval", C.c_int32), ("n_params", C.c_int32),
               ("terminal_cost", C.c_int32), ("reserved", C.c_int32), ("T", C.c_double),
-              ("params", C.c_double * MAX_PARAMS)]
+              ("params", C.c_double * MAX_PARAMS),
+              ("node_num_hidden", C.c_int32), ("node_hidden", C.c_int32 * (MAX_NODE_LAYERS - 1)),
+              ("theta", C.c_void_p), ("theta_doubles", C.c_int64)]
 
 
 class MyrSizes(C.Structure):
@@ -97,11 +101,24 @@ def check(rc: int) -> None:
 
 
 def make_desc(system: str, optimizer: int, method: str, intervals: int, cpi: int = 1, T: float = 0.0, params=None,
-              terminal_cost: bool = False) -> MyrDesc:
+              terminal_cost: bool = False, hidden=None, theta_ptr: int = 0, theta_doubles: int = 0, keepalive=None) -> MyrDesc:
+  """hidden / theta_ptr / theta_doubles: NODE systems ("NODE_<true system>") only; theta_ptr is a device pointer for the
+  device entry points (host pointer for myr_host_*); ``keepalive`` (the tensor / array owning it) is pinned to the struct."""
   d = MyrDesc()
-  if system not in SYSTEM_IDS:
+  node = system.startswith("NODE_")
+  base = system[5:] if node else system
+  if base not in SYSTEM_IDS:
     raise KeyError(f"system {system} has no device implementation")
-  d.system_id = SYSTEM_IDS[system]
+  d.system_id = SYSTEM_IDS[base] + (NODE_BASE if node else 0)
+  if node:
+    if not hidden or len(hidden) > MAX_NODE_LAYERS - 1:
+      raise KeyError(f"NODE systems need 1..{MAX_NODE_LAYERS - 1} hidden layers")
+    d.node_num_hidden = len(hidden)
+    for i, h in enumerate(hidden):
+      d.node_hidden[i] = int(h)
+    d.theta = int(theta_ptr)
+    d.theta_doubles = int(theta_doubles)
+    d._keepalive = keepalive
   d.optimizer = int(optimizer)
   d.integration_method = METHOD_IDS[method]
   d.intervals = int(intervals)

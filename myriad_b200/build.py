@@ -21,6 +21,9 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(ROOT, "build")
 LIB = os.path.join(HERE, "libmyriad_b200.so")
 
+# true systems that also get a NodeSystem wrapper (neural-ODE dynamics on the tensor-core path, csrc/node_mlp.cuh)
+NODE_SYSTEMS = ["CARTPOLE", "VANDERPOL", "CANCERTREATMENT"]
+
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 
@@ -80,10 +83,17 @@ def build(force: bool = False, systems=None, jobs: int | None = None, verbose: b
     objs.append(obj)
     if force or not os.path.exists(obj) or os.path.getmtime(obj) < sys_src_t:
       tasks.append((s, [nvcc, *flags, f"-DMYR_SYS_CLASS={gen[s]}", "-c", os.path.join(CSRC, "sys_unit.cu"), "-o", obj]))
+  node_names = [s for s in NODE_SYSTEMS if s in names]
+  for s in node_names:
+    obj = os.path.join(BUILD, f"node_{s}.o")
+    objs.append(obj)
+    if force or not os.path.exists(obj) or os.path.getmtime(obj) < sys_src_t:
+      tasks.append(("node_" + s, [nvcc, *flags, f"-DMYR_SYS_CLASS={gen[s]}", "-DMYR_NODE=1", "-c", os.path.join(CSRC, "sys_unit.cu"), "-o", obj]))
+  xmacro_node = "-DMYR_BUILD_NODE_SYSTEMS(X)=" + " ".join(f"X({gen[s]})" for s in node_names)
   api_obj = os.path.join(BUILD, "api.o")
   objs.append(api_obj)
   if force or not os.path.exists(api_obj) or os.path.getmtime(api_obj) < src_t or prev != tag:
-    tasks.append(("api", [nvcc, *flags, xmacro, "-c", os.path.join(CSRC, "api.cu"), "-o", api_obj]))
+    tasks.append(("api", [nvcc, *flags, xmacro, xmacro_node, "-c", os.path.join(CSRC, "api.cu"), "-o", api_obj]))
   if tasks:
     if verbose:
       print(f"[myriad_b200.build] compiling {len(tasks)} unit(s) with {jobs} job(s): {[t[0] for t in tasks]}", flush=True)

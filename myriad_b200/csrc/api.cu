@@ -15,6 +15,7 @@ int fail(int code, const char* fmt, const char* a, long long v) {
 }
 
 double system_default_T(int id) {
+  if (id >= MYR_SYS_NODE_BASE) id -= MYR_SYS_NODE_BASE;  // NodeSystem takes T from the true system
   switch (id) {  // T of each system's constructor
     case MYR_SYS_SIMPLECASE: return 1.0;
     case MYR_SYS_CARTPOLE: return 2.0;
@@ -43,9 +44,20 @@ using namespace myr;
 MYR_BUILD_SYSTEMS(MYR_DECL)
 #undef MYR_DECL
 
+// NodeSystem wrappers compiled into this build (build.py passes the list)
+#ifndef MYR_BUILD_NODE_SYSTEMS
+#define MYR_BUILD_NODE_SYSTEMS(X)
+#endif
+#define MYR_DECL(SYS) extern "C" const myr::SysVTable* myr_vtable_node_##SYS(void);
+MYR_BUILD_NODE_SYSTEMS(MYR_DECL)
+#undef MYR_DECL
+
 static const SysVTable* find_system(int id) {
 #define MYR_TRY(SYS) if (SYS::id == id) return myr_vtable_##SYS();
   MYR_BUILD_SYSTEMS(MYR_TRY)
+#undef MYR_TRY
+#define MYR_TRY(SYS) if (MYR_SYS_NODE_BASE + SYS::id == id) return myr_vtable_node_##SYS();
+  MYR_BUILD_NODE_SYSTEMS(MYR_TRY)
 #undef MYR_TRY
   fail(MYR_E_BADARG, "unknown or not-built system_id %s%lld", "", id);
   return nullptr;

@@ -5,6 +5,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #pragma nv_diag_suppress 177   // generated system code declares symbols it may not use
 #pragma nv_diag_suppress 550
 
@@ -13,6 +15,17 @@
 namespace myr {
 
 constexpr int kMaxParams = 16;
+constexpr int kMaxMlpLayers = 5;    // == MYR_MAX_NODE_LAYERS: Linear layers of a NODE MLP (hidden + output)
+constexpr int kMaxMlpWidth = 128;   // == MYR_MAX_NODE_WIDTH
+
+// NODE dynamics (node_mlp.cuh): layer sizes and offsets into the caller's weight vector theta
+struct MlpDesc {
+  int L;                          // number of Linear layers; 0 = analytic dynamics
+  int hp;                         // widest hidden layer rounded up to a multiple of 8
+  int size[kMaxMlpLayers + 1];    // size[0] = n + m, size[1..L-1] hidden widths, size[L] = n
+  int woff[kMaxMlpLayers], boff[kMaxMlpLayers];
+  const double* theta;
+};
 
 enum Method : int { EULER = 0, HEUN = 1, MIDPOINT = 2, RK4 = 3 };
 enum Optimizer : int { OPT_SHOOTING = 0, OPT_TRAPEZOIDAL = 1, OPT_HERMITE_SIMPSON = 2 };
@@ -29,6 +42,7 @@ struct Problem {
   double T;
   double h;       // T / N (collocation) or T / (N * cpi) (shooting step)
   double p[kMaxParams];
+  MlpDesc mlp;
 };
 
 __host__ __device__ __forceinline__ constexpr int packed_size(int n) { return n * (n + 1) / 2; }

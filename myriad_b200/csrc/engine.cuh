@@ -36,9 +36,12 @@ struct scheme_is_lifted<S, typename std::enable_if<S::kLifted>::type> { static c
 // ------------------------------------------------------------------ workspace layout (doubles / instance)
 template <class S>
 struct Layout {
+  // collocation on a NODE system: the MLP is evaluated for all nodes of the instance cooperatively (node_mlp.cuh)
+  static constexpr bool kCoopMlp = sys_is_node<typename S::System>::value && !scheme_is_lifted<S>::value;
   int Q, St;
   int G, F, W, Hinv, gl, phi, psi, rb, dz, dzL, dzU, c, dlam;
   int crD, crU, crVL, crVU, crb, crx;
+  int dynf, dynJ, dynH;   // NODE systems: per-node MLP dynamics values / Jacobians / contracted Hessians
   int ext;
   int total;
   MYR_HDI explicit Layout(const Problem& P) {
@@ -63,6 +66,12 @@ struct Layout {
     crVU = o; o += St * S::NC * S::NC;
     crb = o; o += St * S::NC;
     crx = dlam;  // CR writes its solution straight into dlam
+    dynf = dynJ = dynH = o;
+    if (kCoopMlp) {
+      dynf = o; o += Q * S::n;
+      dynJ = o; o += Q * S::n * S::NW;
+      dynH = o; o += Q * S::NWP;
+    }
     // lifted schemes keep their internal iterate / bounds / multipliers in the workspace too
     ext = o;
     if (scheme_is_lifted<S>::value) o += 6 * Q * S::NW + St * S::NC;
@@ -91,10 +100,20 @@ MYR_HDI Bnd make_bnd(double lb, double ub, double relax) {
 // Evaluates every node at point z (reference layout), stores node arrays in the workspace and returns the
 // objective.  MODE as in schemes.cuh.  zsrc may be the iterate or a trial point.
 template <class S, int MODE>
-MYR_HDI double eval_nodes(const Problem& P, const Layout<S>& L, const double* z, const double* lam, double* w, double* red) {
+MYR_HDI double eval_nodes(const Problem& P, const Layout<S>& L, const double* z, const double* lam, double* w, double* red,
+                          double* mlp_scr = nullptr) {
   const int Q = L.Q;
   double fsum = 0.0;
+  bool have_pre = false;
+#ifdef __CUDA_ARCH__
+  if constexpr (Layout<S>::kCoopMlp) {
+    mlp_nodes_pass<S, MODE>(P, Q, z, lam, w + L.dynf, w + L.dynJ, w + L.dynH, mlp_scr);
+    have_pre = true;
+  }
+#endif
   for (int q = MYR_TID; q < Q; q += MYR_NT) {
+    PreDyn pre;
+    if (have_pre) { pre.f = w + L.dynf + q * S::n; pre.J = w + L.dynJ + q * S::n * S::NW; pre.H = w + L.dynH + q * S::NWP; }
     double v[S::NW], lp[S::NC], ls[S::NC];
 #pragma unroll
     for (int i = 0; i < S::NW; ++i) v[i] = z[S::zidx(P, q, i)];
@@ -107,7 +126,7 @@ MYR_HDI double eval_nodes(const Problem& P, const Layout<S>& L, const double* z,
       }
     }
     double ell, gl[S::NW], phi[S::NC], psi[S::NC], G[S::NC * S::NW], F[S::NC * S::NW], W[S::NWP];
-    S::template eval_node<MODE>(P, q, v, lp, ls, ell, gl, phi, psi, G, F, W);
+    S::template eval_node<MODE>(P, q, v, lp, ls, ell, gl, phi, psi, G, F, W, pre);
     fsum += ell;
 #pragma unroll
     for (int r = 0; r < S::NC; ++r) { w[L.phi + q * S::NC + r] = phi[r]; w[L.psi + q * S::NC + r] = psi[r]; }
@@ -722,7 +741,7 @@ struct InstResult { double f, E0, cinf; int status, iters; };
 
 template <class S>
 MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const InstPtrs& ip, double* cr, double* red,
-                                      double* sig_sh /*Q*NW doubles*/, uint32_t* fix_sh /*Q*/) {
+                                      double* sig_sh /*Q*NW doubles*/, uint32_t* fix_sh /*Q*/, double* mlp_scr = nullptr) {
   constexpr int NW = S::NW, NC = S::NC;
   const Layout<S> L(P);
   const int Q = L.Q, St = L.St;
@@ -773,7 +792,7 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
 
   while (true) {
     // ---------------- K1: evaluate with derivatives
-    f = eval_nodes<S, 2>(P, L, z, lam, w, red);
+    f = eval_nodes<S, 2>(P, L, z, lam, w, red, mlp_scr);
     stage_constraints<S>(P, L, w, w + L.c, red, cinf, c1);
     // ---------------- dual residual, complementarity, scaling sums
     double rdmax = 0.0, szmax = -INFINITY, szmin = INFINITY, sumz = 0.0, nbnd = 0.0, slog = 0.0;
@@ -956,7 +975,7 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
         }
       }
       MYR_SYNC();
-      f_t = eval_nodes<S, 0>(P, L, zt, lam, w, red);
+      f_t = eval_nodes<S, 0>(P, L, zt, lam, w, red, mlp_scr);
       double ci_t, c1_t;
       stage_constraints<S>(P, L, w, w + L.crb /*scratch*/, red, ci_t, c1_t);
       blog = block_sum(blog, red);
@@ -1004,11 +1023,12 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
 // Collocation: the IPM works directly on the caller's arrays.
 template <class S>
 MYR_HDI typename std::enable_if<!scheme_is_lifted<S>::value>::type
-ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, double* cr, double* red, double* sig_sh, uint32_t* fix_sh) {
+ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, double* cr, double* red, double* sig_sh, uint32_t* fix_sh,
+                double* mlp_scr = nullptr) {
   const long long nv = P.nvars, nc = P.ncon;
   InstPtrs ip{io.z0 + b * nv, io.lb + b * nv, io.ub + b * nv, io.z + b * nv, io.lam + b * nc, io.zL + b * nv, io.zU + b * nv,
               io.work + (long long)b * io.work_stride, P.nvars, P.ncon};
-  const InstResult r = ipm_solve_instance<S>(P, O, ip, cr, red, sig_sh, fix_sh);
+  const InstResult r = ipm_solve_instance<S>(P, O, ip, cr, red, sig_sh, fix_sh, mlp_scr);
   if (MYR_TID == 0) {
     io.obj[b] = r.f; io.kkt_err[b] = r.E0; io.con_inf[b] = r.cinf; io.status[b] = r.status; io.iters[b] = r.iters;
   }
@@ -1018,7 +1038,8 @@ ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, doub
 // objective / constraint violation of the REFERENCE NLP (rollouts from the interval-start states).
 template <class S>
 MYR_HDI typename std::enable_if<scheme_is_lifted<S>::value>::type
-ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, double* cr, double* red, double* sig_sh, uint32_t* fix_sh) {
+ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, double* cr, double* red, double* sig_sh, uint32_t* fix_sh,
+                double* = nullptr) {
   constexpr int n = S::n, m = S::m, NW = S::NW, NC = S::NC;
   const Layout<S> L(P);
   const int Q = L.Q, St = L.St;

@@ -37,6 +37,29 @@ static int make_problem(const MyrDesc* d, int B, Problem& P) {
     if (d->n_params != Sys::np) return fail(MYR_E_BADARG, "n_params does not match system %s (%lld given)", Sys::name, d->n_params);
     for (int i = 0; i < Sys::np; ++i) P.p[i] = d->params[i];
   }
+  if (sys_is_node<Sys>::value) {
+    const int k = d->node_num_hidden;
+    if (k < 1 || k > kMaxMlpLayers - 1) return fail(MYR_E_BADARG, "node_num_hidden must be 1..4 (got %s%lld)", "", k);
+    if (!d->theta) return fail(MYR_E_BADARG, "NODE system %s needs theta (MLP weights)", Sys::name);
+    MlpDesc& M = P.mlp;
+    M.L = k + 1;
+    M.size[0] = Sys::n + Sys::m;
+    M.hp = 8;
+    for (int j = 0; j < k; ++j) {
+      const int h = d->node_hidden[j];
+      if (h < 1 || h > kMaxMlpWidth) return fail(MYR_E_BADARG, "hidden layer width must be 1..128 (got %s%lld)", "", h);
+      M.size[j + 1] = h;
+      if ((h + 7) / 8 * 8 > M.hp) M.hp = (h + 7) / 8 * 8;
+    }
+    M.size[k + 1] = Sys::n;
+    long long off = 0;
+    for (int j = 0; j <= k; ++j) {
+      M.woff[j] = (int)off; off += (long long)M.size[j] * M.size[j + 1];
+      M.boff[j] = (int)off; off += M.size[j + 1];
+    }
+    if (d->theta_doubles != off) return fail(MYR_E_BADARG, "theta_doubles does not match the layer sizes (%s%lld expected)", "", off);
+    M.theta = d->theta;
+  }
   return MYR_OK;
 }
 
@@ -90,7 +113,8 @@ static int cuda_check(const char* what) {
   return MYR_OK;
 }
 
-static int threads_for(int Q) {
+static int threads_for(int Q, bool coop_mlp = false) {
+  if (coop_mlp) return 256;  // 8 warps: one 8-row tile of a 64-wide layer each (node_mlp.cuh)
   int t = (Q + 31) / 32 * 32;
   if (t < 32) t = 32;
   if (t > 256) t = 256;
@@ -255,11 +279,19 @@ __global__ void __launch_bounds__(256) eval_kernel(Problem P, const double* __re
   double* sJ = spsi + Q * NC;             // St * ROWP
   double* sH = sJ + (size_t)St * ROWP;    // Q * NWP (only when the Hessian is requested)
   const bool want_h = lam_all && H_out;
+  // NODE systems: per-node MLP outputs + the tensor-core pass's scratch live behind the other regions
+  double* sDyn = sH + ((lam_all && H_out) ? (size_t)Q * S::NWP : 0);
+  double* sScr = sDyn + (size_t)Q * (S::n + S::n * NW + S::NWP);
   const long long jstride = (long long)St * ROW;
   for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
     const double* z = z_all + (long long)b * P.nvars;
     const double* lam = lam_all ? lam_all + (long long)b * P.ncon : nullptr;
     double fsum = 0.0;
+    if constexpr (Layout<S>::kCoopMlp) {
+      double* df = sDyn; double* dJ = df + Q * S::n; double* dH = dJ + Q * S::n * NW;
+      if (want_h) mlp_nodes_pass<S, 2>(P, Q, z, lam, df, dJ, dH, sScr);
+      else mlp_nodes_pass<S, 1>(P, Q, z, lam, df, dJ, dH, sScr);
+    }
     for (int q = threadIdx.x; q < Q; q += blockDim.x) {
       double v[NW], lp[NC], ls[NC];
 #pragma unroll
@@ -270,9 +302,11 @@ __global__ void __launch_bounds__(256) eval_kernel(Problem P, const double* __re
         lp[r] = (want_h && jp >= 0) ? lam[S::cidx(P, jp, r)] : 0.0;
         ls[r] = (want_h && js >= 0) ? lam[S::cidx(P, js, r)] : 0.0;
       }
+      PreDyn pre;
+      if constexpr (Layout<S>::kCoopMlp) { pre.f = sDyn + q * S::n; pre.J = sDyn + Q * S::n + q * S::n * NW; pre.H = sDyn + Q * (S::n + S::n * NW) + q * S::NWP; }
       double ell, gl[NW], phi[NC], psi[NC], G[BLK], F[BLK], W[S::NWP];
-      if (want_h) S::template eval_node<2>(P, q, v, lp, ls, ell, gl, phi, psi, G, F, W);
-      else S::template eval_node<1>(P, q, v, lp, ls, ell, gl, phi, psi, G, F, W);
+      if (want_h) S::template eval_node<2>(P, q, v, lp, ls, ell, gl, phi, psi, G, F, W, pre);
+      else S::template eval_node<1>(P, q, v, lp, ls, ell, gl, phi, psi, G, F, W, pre);
       fsum += ell;
 #pragma unroll
       for (int r = 0; r < NC; ++r) { sphi[q * NC + r] = phi[r]; spsi[q * NC + r] = psi[r]; }
@@ -352,10 +386,12 @@ int sys_eval(const MyrDesc* desc, int B, const double* z, const double* lam, dou
     if (!z) return fail(MYR_E_BADARG, "z is null%s", "");
     const Layout<S> L(P);
     const size_t row = (size_t)S::kMaxStageNodes * S::NC * S::NW + 1;
-    const size_t sm = (64 + 2 * (size_t)L.Q * S::NC + (Jblk ? (size_t)L.St * row : 0) + ((lam && Hblk) ? (size_t)L.Q * S::NWP : 0)) * sizeof(double);
+    size_t smd = 64 + 2 * (size_t)L.Q * S::NC + (Jblk ? (size_t)L.St * row : 0) + ((lam && Hblk) ? (size_t)L.Q * S::NWP : 0);
+    if (Layout<S>::kCoopMlp) smd += (size_t)L.Q * (S::n + S::n * S::NW + S::NWP) + mlp_scratch_doubles<S>(P.mlp);
+    const size_t sm = smd * sizeof(double);
     if (sm > 200 * 1024) return fail(MYR_E_UNSUPPORTED, "problem too large for the shared-memory staged K1 (%s%lld bytes)", "", (long long)sm);
     if (sm > 48 * 1024) cudaFuncSetAttribute(eval_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    eval_kernel<S><<<B, threads_for(L.Q), sm, (cudaStream_t)stream>>>(P, z, lam, f, grad, c, Jblk, Hblk);
+    eval_kernel<S><<<B, threads_for(L.Q, Layout<S>::kCoopMlp), sm, (cudaStream_t)stream>>>(P, z, lam, f, grad, c, Jblk, Hblk);
     return cuda_check("myr_eval");
   });
 }
@@ -436,7 +472,11 @@ struct SmemPlan {
     fix = (((size_t)L.Q * sizeof(uint32_t)) + 15) & ~(size_t)15;
     cr = (size_t)L.cr_doubles() * sizeof(double);
     cr_in_smem = red + sig + fix + cr <= budget;
-    total = red + sig + fix + (cr_in_smem ? cr : 0);
+    // the MLP pass's scratch (NODE systems) aliases the CR scratch: the two are never live at the same time
+    const size_t mlp = Layout<S>::kCoopMlp ? (size_t)mlp_scratch_doubles<S>(P.mlp) * sizeof(double) : 0;
+    size_t scratch = cr_in_smem ? cr : 0;
+    if (mlp > scratch) scratch = mlp;
+    total = red + sig + fix + scratch;
   }
 };
 
@@ -522,7 +562,7 @@ __global__ void __launch_bounds__(256) ipm_kernel(Problem P, IpmOpts O, IpmIO io
   double* crs = reinterpret_cast<double*>(reinterpret_cast<char*>(fix) + ((((size_t)L.Q * sizeof(uint32_t)) + 15) & ~(size_t)15));
   for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
     double* cr = cr_in_smem ? crs : io.work + (long long)b * io.work_stride + L.crD;
-    ipm_solve_entry<S>(P, O, io, b, cr, red, sig, fix);
+    ipm_solve_entry<S>(P, O, io, b, cr, red, sig, fix, crs);
     __syncthreads();
   }
 }
@@ -542,7 +582,7 @@ int sys_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const doub
     const IpmOpts O = make_opts(opts);
     const SmemPlan<S> sp(P);
     if (sp.total > 48 * 1024) cudaFuncSetAttribute(ipm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
-    ipm_kernel<S><<<B, threads_for(L.Q), sp.total, (cudaStream_t)stream>>>(P, O, io, sp.cr_in_smem ? 1 : 0);
+    ipm_kernel<S><<<B, threads_for(L.Q, Layout<S>::kCoopMlp), sp.total, (cudaStream_t)stream>>>(P, O, io, sp.cr_in_smem ? 1 : 0);
     return cuda_check("myr_ipm_solve");
   });
 }
@@ -594,11 +634,18 @@ int sys_host_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double*
   return (int)MYR_OK;
 }
 
+// the verification rollout of a NodeSystem integrates the TRUE dynamics (node_system.py:32-33, useful_scripts.py:47-49)
+template <class Sys, class = void>
+struct rollout_system { using type = Sys; };
+template <class Sys>
+struct rollout_system<Sys, typename std::enable_if<Sys::kNode>::type> { using type = typename Sys::TrueSystem; };
+
 template <class Sys>
 SysVTable make_vtable() {
+  using R = typename rollout_system<Sys>::type;
   return SysVTable{Sys::id, Sys::name, &sys_problem_sizes<Sys>, &sys_eval<Sys>, &sys_host_eval<Sys>, &sys_kkt_solve<Sys>,
-                   &sys_host_kkt_solve<Sys>, &sys_ipm_solve<Sys>, &sys_host_ipm_solve<Sys>, &sys_rollout_cost<Sys>,
-                   &sys_host_rollout_cost<Sys>};
+                   &sys_host_kkt_solve<Sys>, &sys_ipm_solve<Sys>, &sys_host_ipm_solve<Sys>, &sys_rollout_cost<R>,
+                   &sys_host_rollout_cost<R>};
 }
 
 }  // namespace myr

@@ -19,8 +19,18 @@
 // constraint vector) and nodes/stages, plus eval_node<MODE>().
 #pragma once
 #include "common.cuh"
+#include "node_mlp.cuh"
 
 namespace myr {
+
+// Collocation on a NODE system never evaluates the MLP per thread on the device: the cooperative tensor-core pass
+// (mlp_nodes_pass) has filled PreDyn for every node.  Compiling the scalar fallback out of device code keeps the
+// kernels' stack frames small.
+#ifdef __CUDA_ARCH__
+#define MYR_DIRECT_DYN(call) do { if constexpr (!sys_is_node<Sys>::value) { call; } } while (0)
+#else
+#define MYR_DIRECT_DYN(call) do { call; } while (0)
+#endif
 
 // MODE: 0 = values only (ell, phi, psi); 1 = + first derivatives (gl, G, F); 2 = + Hessian block W
 // W (packed upper NW) = hess( ell + lam_phi . phi + lam_psi . psi ) w.r.t. v.
@@ -51,9 +61,18 @@ struct Trapezoid {
   MYR_HDI static int phi_slot(const Problem&, int) { return 0; }
   MYR_HDI static int psi_slot(const Problem&, int) { return 1; }
 
+  // weights of the dynamics Hessians in the node's Lagrangian block: mu_i = d (lam . c) / d f_i(v_q);
+  // lam = the instance's multipliers in the reference's constraint order
+  MYR_HDI static void node_mu(const Problem& P, int q, const double* lam, double* mu) {
+    const double hh = 0.5 * P.h;
+#pragma unroll
+    for (int i = 0; i < n; ++i) mu[i] = hh * ((q < P.N ? lam[q * n + i] : 0.0) + (q >= 1 ? lam[(q - 1) * n + i] : 0.0));
+  }
+
   template <int MODE>
   MYR_HDI static void eval_node(const Problem& P, int q, const double* v, const double* lam_phi, const double* lam_psi,
-                                double& ell, double* gl, double* phi, double* psi, double* G, double* F, double* W) {
+                                double& ell, double* gl, double* phi, double* psi, double* G, double* F, double* W,
+                                const PreDyn& pre = PreDyn()) {
     const double h = P.h;
     const double hh = 0.5 * h;
     const bool has_phi = q < P.N, has_psi = q >= 1;
@@ -61,20 +80,36 @@ struct Trapezoid {
     const double t = (q == P.N) ? P.T : q * h;       // jnp.linspace(0, T, N+1)[q]
     double f[n];
     if (MODE == 0) {
-      Sys::f(v, v + n, P.p, f);
+      if (pre.f) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) f[i] = pre.f[i];
+      } else {
+        MYR_DIRECT_DYN(dyn_f<Sys>(P, v, v + n, f));
+      }
       ell = wq * Sys::cost(v, v + n, t, P.p);
     } else {
       double J[n * NW];
+      if (pre.f) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) f[i] = pre.f[i];
+#pragma unroll
+        for (int i = 0; i < n * NW; ++i) J[i] = pre.J[i];
+      }
       if (MODE == 2) {
-        double mu[n];
+        if (pre.f) {
 #pragma unroll
-        for (int i = 0; i < n; ++i) mu[i] = hh * ((has_phi ? lam_phi[i] : 0.0) + (has_psi ? lam_psi[i] : 0.0));
+          for (int i = 0; i < NWP; ++i) W[i] = pre.H[i];
+        } else {
+          double mu[n];
 #pragma unroll
-        for (int i = 0; i < NWP; ++i) W[i] = 0.0;
-        Sys::fjac_hess(v, v + n, P.p, mu, f, J, W);
+          for (int i = 0; i < n; ++i) mu[i] = hh * ((has_phi ? lam_phi[i] : 0.0) + (has_psi ? lam_psi[i] : 0.0));
+#pragma unroll
+          for (int i = 0; i < NWP; ++i) W[i] = 0.0;
+          MYR_DIRECT_DYN(dyn_fjac_hess<Sys>(P, v, v + n, mu, f, J, W));
+        }
         ell = wq * Sys::cost_grad_hess(v, v + n, t, P.p, wq, gl, W);
       } else {
-        Sys::fjac(v, v + n, P.p, f, J);
+        if (!pre.f) { MYR_DIRECT_DYN(dyn_fjac<Sys>(P, v, v + n, f, J)); }
         ell = wq * Sys::cost_grad(v, v + n, t, P.p, gl);
       }
 #pragma unroll
@@ -119,9 +154,24 @@ struct HermiteSimpson {
   MYR_HDI static int phi_slot(const Problem&, int q) { return q & 1; }
   MYR_HDI static int psi_slot(const Problem&, int) { return 2; }
 
+  MYR_HDI static void node_mu(const Problem& P, int q, const double* lam, double* mu) {
+    const double h = P.h;
+    const bool mid = (q & 1);
+    const bool has_phi = q < 2 * P.N, has_psi = (!mid) && q >= 2;
+    const int jp = q / 2, js = q / 2 - 1;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      double a = 0.0;
+      if (has_phi) a += (mid ? -4.0 * h / 6.0 : -h / 6.0) * lam[cidx(P, jp, i)] + (mid ? 0.0 : -h / 8.0) * lam[cidx(P, jp, n + i)];
+      if (has_psi) a += (-h / 6.0) * lam[cidx(P, js, i)] + (h / 8.0) * lam[cidx(P, js, n + i)];
+      mu[i] = a;
+    }
+  }
+
   template <int MODE>
   MYR_HDI static void eval_node(const Problem& P, int q, const double* v, const double* lam_phi, const double* lam_psi,
-                                double& ell, double* gl, double* phi, double* psi, double* G, double* F, double* W) {
+                                double& ell, double* gl, double* phi, double* psi, double* G, double* F, double* W,
+                                const PreDyn& pre = PreDyn()) {
     const double h = P.h;
     const bool mid = (q & 1);
     const bool has_phi = q < 2 * P.N, has_psi = (!mid) && q >= 2;
@@ -137,25 +187,41 @@ struct HermiteSimpson {
     const double cf_psi_d = -h / 6.0, cx_psi_d = 1.0, cf_psi_i = h / 8.0, cx_psi_i = -0.5;
     double f[n];
     if (MODE == 0) {
-      Sys::f(v, v + n, P.p, f);
+      if (pre.f) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) f[i] = pre.f[i];
+      } else {
+        MYR_DIRECT_DYN(dyn_f<Sys>(P, v, v + n, f));
+      }
       ell = wq * Sys::cost(v, v + n, t, P.p);
     } else {
       double J[n * NW];
+      if (pre.f) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) f[i] = pre.f[i];
+#pragma unroll
+        for (int i = 0; i < n * NW; ++i) J[i] = pre.J[i];
+      }
       if (MODE == 2) {
-        double mu[n];
+        if (pre.f) {
 #pragma unroll
-        for (int i = 0; i < n; ++i) {
-          double a = 0.0;
-          if (has_phi) a += cf_phi_d * lam_phi[i] + cf_phi_i * lam_phi[n + i];
-          if (has_psi) a += cf_psi_d * lam_psi[i] + cf_psi_i * lam_psi[n + i];
-          mu[i] = a;
+          for (int i = 0; i < NWP; ++i) W[i] = pre.H[i];
+        } else {
+          double mu[n];
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            double a = 0.0;
+            if (has_phi) a += cf_phi_d * lam_phi[i] + cf_phi_i * lam_phi[n + i];
+            if (has_psi) a += cf_psi_d * lam_psi[i] + cf_psi_i * lam_psi[n + i];
+            mu[i] = a;
+          }
+#pragma unroll
+          for (int i = 0; i < NWP; ++i) W[i] = 0.0;
+          MYR_DIRECT_DYN(dyn_fjac_hess<Sys>(P, v, v + n, mu, f, J, W));
         }
-#pragma unroll
-        for (int i = 0; i < NWP; ++i) W[i] = 0.0;
-        Sys::fjac_hess(v, v + n, P.p, mu, f, J, W);
         ell = wq * Sys::cost_grad_hess(v, v + n, t, P.p, wq, gl, W);
       } else {
-        Sys::fjac(v, v + n, P.p, f, J);
+        if (!pre.f) { MYR_DIRECT_DYN(dyn_fjac<Sys>(P, v, v + n, f, J)); }
         ell = wq * Sys::cost_grad(v, v + n, t, P.p, gl);
       }
 #pragma unroll

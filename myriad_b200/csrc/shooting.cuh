@@ -21,6 +21,7 @@
 // stage (k+1)*cpi-1 is the reference's multiplier of constraint block k (same sign: px - x_next).
 #pragma once
 #include "common.cuh"
+#include "node_mlp.cuh"
 
 namespace myr {
 
@@ -79,7 +80,8 @@ struct ShootingLifted {
   // ---- one explicit Runge-Kutta step with first/second derivatives w.r.t. the node block v
   template <int MODE>
   MYR_HDI static void eval_node(const Problem& P, int q, const double* v, const double* lam_phi, const double* lam_psi,
-                                double& ell, double* gl, double* phi, double* psi, double* Gm, double* Fm, double* W) {
+                                double& ell, double* gl, double* phi, double* psi, double* Gm, double* Fm, double* W,
+                                const PreDyn& = PreDyn()) {
     const int Gn = G(P);
     const bool has_phi = q < Gn, has_psi = q >= 1;
     const double h = P.h;
@@ -146,10 +148,10 @@ struct ShootingLifted {
         uk[c][j] = u;
       }
       if (MODE == 0) {
-        Sys::f(xk[c], uk[c], P.p, kk[c]);
+        dyn_f<Sys>(P, xk[c], uk[c], kk[c]);
         gval[c] = Sys::cost(xk[c], uk[c], t0 + tc[c] * h, P.p);
       } else {
-        Sys::fjac(xk[c], uk[c], P.p, kk[c], Aj[c]);
+        dyn_fjac<Sys>(P, xk[c], uk[c], kk[c], Aj[c]);
         gval[c] = Sys::cost_grad(xk[c], uk[c], t0 + tc[c] * h, P.p, gyc[c]);
         // X_c = [I 0] + h a_c K_{c-1}
 #pragma unroll
@@ -237,7 +239,7 @@ struct ShootingLifted {
 #pragma unroll
       for (int i = 0; i < (n + m) * (n + m + 1) / 2; ++i) Hy[i] = 0.0;
       double fd[n], Jd[n * (n + m)], gd[n + m];
-      Sys::fjac_hess(xk[c], uk[c], P.p, ab[c], fd, Jd, Hy);
+      dyn_fjac_hess<Sys>(P, xk[c], uk[c], ab[c], fd, Jd, Hy);
       Sys::cost_grad_hess(xk[c], uk[c], t0 + tc[c] * h, P.p, h * bw[c], gd, Hy);
       // Y_c rows: x rows = Xs[c], u rows j: e_{n+s*m+j} * cu[c][s]
       // T = Hy * Y  ((n+m) x NW), then W += Y^T T

@@ -23,7 +23,8 @@ _ENGINES: Dict[tuple, Engine] = {}
 
 def _engine_for(tr) -> Engine:
   d = tr.desc()
-  key = (d.system_id, d.optimizer, d.integration_method, d.intervals, d.controls_per_interval, d.T, tuple(d.params[:d.n_params]))
+  key = (d.system_id, d.optimizer, d.integration_method, d.intervals, d.controls_per_interval, d.T, tuple(d.params[:d.n_params]),
+         d.theta, tuple(d.node_hidden[:d.node_num_hidden]))
   if key not in _ENGINES:
     _ENGINES[key] = Engine(d)
   return _ENGINES[key]

@@ -50,11 +50,21 @@ class Transcription:
       self.ncon = 2 * self.intervals * self.n
     self.nvars = self.nx_nodes * self.n + self.nu_nodes * self.m
 
-  def desc(self, optimizer: Optional[int] = None, intervals: Optional[int] = None, cpi: Optional[int] = None) -> ML.MyrDesc:
+  def desc(self, optimizer: Optional[int] = None, intervals: Optional[int] = None, cpi: Optional[int] = None,
+           device="cuda") -> ML.MyrDesc:
+    """device: where the NODE weights (if any) are placed -- "cuda" for the product path, "host" for the myr_host_* twins."""
     s = self.system
+    extra = {}
+    if getattr(s, "theta", None) is not None:  # NodeSystem
+      if device == "host":
+        th = np.ascontiguousarray(s.theta, dtype=np.float64)
+        extra = dict(hidden=s.hidden, theta_ptr=th.ctypes.data, theta_doubles=th.size, keepalive=th)
+      else:
+        th = s.theta_device(torch.device(device))
+        extra = dict(hidden=s.hidden, theta_ptr=th.data_ptr(), theta_doubles=th.numel(), keepalive=th)
     return ML.make_desc(s.device_name, self.optimizer if optimizer is None else optimizer, self.method,
                         self.intervals if intervals is None else intervals, self.cpi if cpi is None else cpi,
-                        T=float(s.T), params=list(s.params), terminal_cost=bool(s.terminal_cost))
+                        T=float(s.T), params=list(s.params), terminal_cost=bool(s.terminal_cost), **extra)
 
   def unravel(self, z):
     """ravel_pytree((x, u)) inverse; works for numpy arrays and torch tensors, batched or not."""
@@ -75,7 +85,7 @@ def _linspace_rows(a: torch.Tensor, b: torch.Tensor, num: int) -> torch.Tensor:
 
 def _rollout_guess(tr: Transcription, x0s: torch.Tensor, steps: int) -> torch.Tensor:
   """integrate_time_independent(dynamics, x_0, zeros, T/steps, steps, method)[1] -> [B, steps+1, n]"""
-  eng = Engine(tr.desc(optimizer=TRAPEZOIDAL, intervals=steps, cpi=1))
+  eng = Engine(tr.desc(optimizer=TRAPEZOIDAL, intervals=steps, cpi=1, device=x0s.device))
   u = torch.zeros(x0s.shape[0], steps + 1, tr.m, dtype=torch.float64, device=x0s.device)
   xs, _ = eng.rollout_cost(u, x0s, want_states=True)
   return xs

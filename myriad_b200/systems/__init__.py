@@ -66,6 +66,62 @@ class SimpleCaseWithBounds(FiniteHorizonControlSystem):
                      terminal_cost=False, discrete=False, device_name="SIMPLECASEWITHBOUNDS", params=[A, C])
 
 
+class NodeSystem(FiniteHorizonControlSystem):
+  """myriad/systems/neural_ode/node_system.py:14-42: a system whose (parametrized) dynamics is the neural-ODE MLP of
+  myriad/neural_ode/create_node.py:110-117 applied to concat(x, u), while cost, bounds, horizon, start/end states and
+  the post-solve verification rollout are the true system's.
+
+  ``node`` is anything with ``.params`` -- the haiku parameter mapping {'linear': {'w','b'}, 'linear_1': ..., ...}
+  (create_node.py:124-131; flat 'linear/w' keys as in an .npz are accepted too) -- e.g. myriad_b200.neural_ode.NeuralODE.
+  Planning with it (get_optimizer(hp, cfg, NodeSystem(node, system)).solve()) is what the reference does through
+  plan_with_node_model (myriad/utils.py:230-242)."""
+
+  def __init__(self, node, true_system: FiniteHorizonControlSystem) -> None:
+    self.node = node
+    self.true_system = true_system
+    super().__init__(x_0=true_system.x_0, x_T=true_system.x_T, T=true_system.T, bounds=true_system.bounds,
+                     terminal_cost=true_system.terminal_cost, discrete=true_system.discrete,
+                     device_name="NODE_" + true_system.device_name, params=list(true_system.params))
+    self.layers = mlp_layers(node.params if hasattr(node, "params") else node)
+    n_in = self.state_size + self.control_size
+    sizes = [w.shape for w, _ in self.layers]
+    if sizes[0][0] != n_in or sizes[-1][1] != self.state_size or any(a[1] != b[0] for a, b in zip(sizes[:-1], sizes[1:])):
+      raise ValueError(f"MLP layer shapes {sizes} do not map {n_in} inputs to {self.state_size} outputs")
+    self.hidden = [int(w.shape[1]) for w, _ in self.layers[:-1]]
+    # flat weight vector in the order the C ABI documents: per layer w (in, out) row-major, then b
+    self.theta = np.concatenate([np.concatenate([np.asarray(w, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()])
+                                 for w, b in self.layers])
+    self._theta_dev = {}
+
+  def theta_device(self, device):
+    import torch
+    key = str(device)
+    if key not in self._theta_dev:
+      self._theta_dev[key] = torch.as_tensor(self.theta, dtype=torch.float64).to(device).contiguous()
+    return self._theta_dev[key]
+
+
+def mlp_layers(params):
+  """haiku parameter mapping -> [(w (in,out), b (out,)), ...] in layer order linear, linear_1, linear_2, ..."""
+  def get(name):
+    if name in params:
+      p = params[name]
+      return np.asarray(p['w'], dtype=np.float64), np.asarray(p['b'], dtype=np.float64)
+    if name + '/w' in params:
+      return np.asarray(params[name + '/w'], dtype=np.float64), np.asarray(params[name + '/b'], dtype=np.float64)
+    return None
+  out, i = [], 0
+  while True:
+    layer = get('linear' if i == 0 else f'linear_{i}')
+    if layer is None:
+      break
+    out.append(layer)
+    i += 1
+  if len(out) < 2:
+    raise ValueError("expected haiku parameters 'linear', 'linear_1', ... (create_node.py:124-131)")
+  return out
+
+
 class _NotOnDevice:
   def __init__(self, name):
     self.name = name

@@ -72,7 +72,13 @@ class TrajectoryOptimizer(object):
     return self._with_params(params).constraints(variables)
 
   def _with_params(self, params) -> "TrajectoryOptimizer":
-    system = self.hp.system(**params)
+    """params: constructor arguments of the physical system (useful_scripts.py:35), or -- for a NodeSystem -- the haiku
+    parameter mapping of its MLP (NodeSystem.parametrized_dynamics, node_system.py:36-38)."""
+    from myriad_b200.systems import NodeSystem
+    if isinstance(self.system, NodeSystem):
+      system = NodeSystem(params, self.system.true_system)
+    else:
+      system = self.hp.system(**params)
     cfg = Config(**{**self.cfg.__dict__, "verbose": False})
     return type(self)(self.hp, cfg, system)
 

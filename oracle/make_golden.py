@@ -50,14 +50,45 @@ CASES = {
   "s_cancer_hs_10": ("CANCERTREATMENT", "COLLOCATION", "HERMITE_SIMPSON", "RK4", 10, 1),
   "s_cancer_shooting_2x10_midpoint": ("CANCERTREATMENT", "SHOOTING", "TRAPEZOIDAL", "MIDPOINT", 2, 10),
   "s_cancer_shooting_2x10_euler": ("CANCERTREATMENT", "SHOOTING", "TRAPEZOIDAL", "EULER", 2, 10),
+  # BASELINE config C5: CARTPOLE with neural-ODE MLP dynamics (3 x 64), planned the way the reference's
+  # plan_with_node_model does (myriad/utils.py:230-242: system.dynamics <- net.apply(params, append(x, u))).
+  # Weights: tests/golden/node_cartpole_64x64x64.npz (tools/fit_node.py).
+  "c5_node_cartpole_trap_100": ("NODE_CARTPOLE", "COLLOCATION", "TRAPEZOIDAL", "HEUN", 100, 1),
+  "n_node_cartpole_trap_10": ("NODE_CARTPOLE", "COLLOCATION", "TRAPEZOIDAL", "HEUN", 10, 1),
+  "n_node_cartpole_hs_6": ("NODE_CARTPOLE", "COLLOCATION", "HERMITE_SIMPSON", "RK4", 6, 1),
+  "n_node_cartpole_shooting_3x4_heun": ("NODE_CARTPOLE", "SHOOTING", "TRAPEZOIDAL", "HEUN", 3, 4),
 }
+
+NODE_WEIGHTS = {"NODE_CARTPOLE": "node_cartpole_64x64x64.npz"}
+
+
+def load_node_weights(sysname):
+  """-> [(w, b), ...] in haiku layer order (linear, linear_1, ...: create_node.py:124-131)"""
+  d = dict(np.load(os.path.join(GOLD, NODE_WEIGHTS[sysname])))
+  out, i = [], 0
+  while ("linear" if i == 0 else f"linear_{i}") + "/w" in d:
+    k = "linear" if i == 0 else f"linear_{i}"
+    out.append((d[k + "/w"], d[k + "/b"]))
+    i += 1
+  return out
+
+
+def _haiku_mlp_apply(weights, x_and_u):
+  """net.apply(params, x_and_u) of create_node.py:110-117 restated (haiku is not installed): hk.Linear is x @ w + b,
+  jax.nn.sigmoid between layers, linear output."""
+  h = x_and_u
+  for i, (w, b) in enumerate(weights):
+    h = h @ w + b
+    if i + 1 < len(weights):
+      h = 1.0 / (1.0 + np.exp(-h))
+  return h
 
 # which cases also get a reference SLSQP solve (kept to what finishes in minutes)
 SOLVE_CASES = [
   "c2_cartpole_trap_100", "c3_vanderpol_shooting_1x50_heun", "c4_cancer_shooting_1x100_heun",
   "c1_simplecase_shooting_10x100_heun", "t_simplecase_shooting_1x50_heun", "t_simplecase_trap_50",
   "t_simplecase_hs_50", "s_vanderpol_trap_20", "s_cancer_trap_20", "s_cartpole_trap_10",
-  "t_simplecase_shooting_20x3_heun", "s_vanderpol_hs_10",
+  "t_simplecase_shooting_20x3_heun", "s_vanderpol_hs_10", "n_node_cartpole_trap_10",
 ]
 
 
@@ -66,7 +97,9 @@ def _ref_objects(case):
   from myriad.systems import SystemType
   from myriad.trajectory_optimizers import get_optimizer
   sysname, opt, quad, meth, intervals, cpi = CASES[case]
-  hp = HParams(system=SystemType[sysname], optimizer=OptimizerType[opt], nlpsolver=NLPSolverType.SLSQP,
+  node = sysname.startswith("NODE_")
+  true_name = sysname[5:] if node else sysname
+  hp = HParams(system=SystemType[true_name], optimizer=OptimizerType[opt], nlpsolver=NLPSolverType.SLSQP,
                integration_method=IntegrationMethod[meth], quadrature_rule=QuadratureRule[quad],
                intervals=intervals, controls_per_interval=cpi, max_iter=1000)
   cfg = Config(verbose=False, plot=False)
@@ -74,6 +107,10 @@ def _ref_objects(case):
   import io, contextlib
   with contextlib.redirect_stdout(io.StringIO()):  # shooting.py:53 prints
     optimizer = get_optimizer(hp, cfg, system)
+  if node:  # exactly what plan_with_node_model does before calling optimizer.solve() (myriad/utils.py:231-236)
+    import jax.numpy as jnp
+    weights = load_node_weights(sysname)
+    system.dynamics = lambda x, u, t=None: _haiku_mlp_apply(weights, jnp.append(x, u))
   return hp, cfg, system, optimizer
 
 
@@ -107,6 +144,8 @@ def make_eval_fixture(case: str) -> dict:
   # post-solve rollout of the TRUE system under the test-point controls (myriad/utils.py:258-324)
   from myriad.utils import get_defect, get_state_trajectory_and_cost
   _, u = optimizer.unravel(z)
+  if CASES[case][0].startswith("NODE_"):
+    system = hp.system()  # the verification rollout integrates the TRUE system (useful_scripts.py:43-49)
   try:
     xs, c = get_state_trajectory_and_cost(hp, system, system.x_0, u)
     out["rollout_states"] = np.asarray(xs, dtype=np.float64)
@@ -132,6 +171,8 @@ def make_solve_fixture(case: str) -> dict:
   out = {"sol_x": np.asarray(res["x"]), "sol_u": np.asarray(res["u"]), "sol_z": np.asarray(res["xs_and_us"]),
          "sol_cost": np.float64(res["cost"]), "sol_seconds": np.float64(secs),
          "sol_con_inf": np.float64(np.abs(optimizer.constraints(res["xs_and_us"])).max())}
+  if CASES[case][0].startswith("NODE_"):
+    system = hp.system()
   try:
     xs, c = get_state_trajectory_and_cost(hp, system, system.x_0, res["u"])
     out["sol_rollout_cost"] = np.float64(np.squeeze(c))

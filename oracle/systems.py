@@ -193,5 +193,22 @@ SYSTEMS = {
 }
 
 
+def golden_node_weights(name: str):
+  """[(w, b), ...] of the committed NODE fixture weights for system ``NODE_<true system>`` (tests/golden/node_*.npz,
+  made by tools/fit_node.py), haiku layer order linear, linear_1, ... (create_node.py:124-131)."""
+  import os
+  files = {"NODE_CARTPOLE": "node_cartpole_64x64x64.npz"}
+  path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", files[name])
+  d = dict(np.load(path))
+  out, i = [], 0
+  while ("linear" if i == 0 else f"linear_{i}") + "/w" in d:
+    k = "linear" if i == 0 else f"linear_{i}"
+    out.append((d[k + "/w"], d[k + "/b"]))
+    i += 1
+  return out
+
+
 def make_system(name: str, **params) -> OracleSystem:
+  if name.startswith("NODE_"):
+    return NodeSystem(SYSTEMS[name[5:]](**params), golden_node_weights(name))
   return SYSTEMS[name](**params)

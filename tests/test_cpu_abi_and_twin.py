@@ -26,6 +26,9 @@ def ML():
 
 def _desc(ML, case):
   sysname, opt, quad, meth, intervals, cpi = CASES[case]
+  if sysname.startswith("NODE_"):  # NodeSystem: MLP weights passed as a HOST pointer to the host twin
+    from tests.cases import product_transcription
+    return product_transcription(case).desc(device="host")
   optid = ML.OPT_SHOOTING if opt == "SHOOTING" else (ML.OPT_TRAPEZOIDAL if quad == "TRAPEZOIDAL" else ML.OPT_HERMITE_SIMPSON)
   return ML.make_desc(sysname, optid, meth, intervals, cpi)
 
@@ -41,7 +44,7 @@ def test_library_exports_every_declared_symbol(ML):
   lib = ML.lib()
   for name in declared:
     assert getattr(lib, name) is not None
-  assert lib.myr_abi_version() == 1
+  assert lib.myr_abi_version() == 2
 
 
 @pytest.mark.parametrize("case", sorted(CASES))
@@ -205,7 +208,7 @@ def test_host_twin_rollout_matches_reference_fixture(ML, case):
   s = ML.problem_sizes(d)
   sysname, opt, quad, meth, intervals, cpi = CASES[case]
   from oracle.systems import make_system
-  x0 = np.ascontiguousarray(make_system(sysname).x_0[None])
+  x0 = np.ascontiguousarray(np.asarray(make_system(sysname).x_0, dtype=np.float64)[None])
   u = np.ascontiguousarray(fx["z"][s.nx_nodes * s.n:].reshape(1, s.nu_nodes, s.m))
   steps = intervals * (cpi if opt == "SHOOTING" else 1)
   xs = np.zeros((1, steps + 1, s.n)); cost = np.zeros(1)

@@ -67,6 +67,7 @@ def test_post_solve_rollout_matches_reference(case):
   if opt == "COLLOCATION":
     cpi = 1  # HParams.__post_init__ (myriad/config.py:98-99)
   _, u = tr.unravel(fx["z"])
+  system = getattr(system, "true_system", system)  # a NodeSystem's verification rollout integrates the TRUE dynamics
   xs, c = get_state_trajectory_and_cost(system, intervals, cpi, meth, system.x_0, u)
   _close(xs, fx["rollout_states"], rtol=1e-11)
   _close(c, fx["rollout_cost"], rtol=1e-11)
