@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmyriad_b200.so")
+LIB_PATH = os.environ.get("MYR_LIB", os.path.join(HERE, "libmyriad_b200.so"))  # MYR_LIB: A/B builds of the same ABI
 
 MAX_PARAMS = 16
 MAX_NODE_LAYERS = 5

@@ -14,6 +14,10 @@
 
 namespace myr {
 
+#ifdef MYR_PROFILE_PHASES
+__device__ unsigned long long g_phase_cycles[16];  // per-phase cycle / event counters (debug builds)
+#endif
+
 constexpr int kMaxParams = 16;
 constexpr int kMaxMlpLayers = 5;    // == MYR_MAX_NODE_LAYERS: Linear layers of a NODE MLP (hidden + output)
 constexpr int kMaxMlpWidth = 128;   // == MYR_MAX_NODE_WIDTH
@@ -239,7 +243,11 @@ MYR_HDI bool sym_inverse_inertia_fast(const double* A, uint32_t mask, double* in
       a[i][j] = v;
       scale = fmax(scale, fabs(v));
     }
-  const double thresh = 1e-7 * scale;
+  // A 1x1 pivot is accepted when it bounds the multipliers of its own column (|d_k| > 1e-7 max_i |v_ik|, the
+  // Bunch-Kaufman test with a loose alpha) and is not numerically zero against the block; a small diagonal entry whose
+  // column is (nearly) decoupled -- e.g. a state that enters neither cost nor dynamics and sits far from its bounds, so
+  // that only a tiny barrier term is on its diagonal -- is a perfectly good pivot and must not force the slow path.
+  const double tiny = 1e-14 * scale;
   double d[N], l[N][N];
   bool ok = true;
   int np_ = 0, nn_ = 0;
@@ -250,18 +258,20 @@ MYR_HDI bool sym_inverse_inertia_fast(const double* A, uint32_t mask, double* in
 #pragma unroll
     for (int j = 0; j < k; ++j) dk -= l[k][j] * l[k][j] * d[j];
     d[k] = dk;
-    ok = ok && (fabs(dk) > thresh);
     minpiv = fmin(minpiv, fabs(dk));
     const bool masked = (mask >> k) & 1u;
     if (!masked) { if (dk > 0) ++np_; else ++nn_; }
     const double rk = 1.0 / dk;
+    double colmax = 0.0;
 #pragma unroll
     for (int i = k + 1; i < N; ++i) {
       double v = a[i][k];
 #pragma unroll
       for (int j = 0; j < k; ++j) v -= l[i][j] * l[k][j] * d[j];
+      colmax = fmax(colmax, fabs(v));
       l[i][k] = v * rk;
     }
+    ok = ok && (fabs(dk) > 1e-7 * colmax) && (fabs(dk) > tiny);
   }
   if (!ok) return false;
   // Linv (unit lower): m = L^-1
@@ -307,7 +317,10 @@ template <int N>
 MYR_HDI void sym_inverse(double* A, uint32_t mask, double* inv, int& npos, int& nneg, int& nzero, double* piv_ratio = nullptr) {
   nzero = 0;
   double pr = 0.0;
-  if (sym_inverse_inertia_fast<N>(A, mask, inv, npos, nneg, pr)) { if (piv_ratio) *piv_ratio = pr; return; }
+  if (sym_inverse_inertia_fast<N>(A, mask, inv, npos, nneg, pr)) {
+    if (piv_ratio) *piv_ratio = pr;
+    return;
+  }
   if (piv_ratio) *piv_ratio = 0.0;  // pivoted fallback: treat as ill-conditioned
   sym_inverse_inertia<N>(A, mask, inv, npos, nneg, nzero);
 }

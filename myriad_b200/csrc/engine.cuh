@@ -33,39 +33,58 @@ struct scheme_is_lifted { static constexpr bool value = false; };
 template <class S>
 struct scheme_is_lifted<S, typename std::enable_if<S::kLifted>::type> { static constexpr bool value = true; };
 
+// ------------------------------------------------------------------ optional per-phase cycle accounting (debug builds)
+// -DMYR_PROFILE_PHASES: thread 0 of every CTA accumulates clock64() deltas per phase into g_phase_cycles (read back
+// with myr_debug_phase_cycles); compiled out of the product build.
+#if defined(MYR_PROFILE_PHASES) && defined(__CUDA_ARCH__)
+#define MYR_PH_DECL long long ph_t0_ = clock64();
+#define MYR_PH(idx) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase_cycles[idx], (unsigned long long)(t_ - ph_t0_)); ph_t0_ = t_; } } while (0)
+#else
+#define MYR_PH_DECL
+#define MYR_PH(idx) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------ workspace layout (doubles / instance)
 template <class S>
 struct Layout {
   // collocation on a NODE system: the MLP is evaluated for all nodes of the instance cooperatively (node_mlp.cuh)
   static constexpr bool kCoopMlp = sys_is_node<typename S::System>::value && !scheme_is_lifted<S>::value;
   int Q, St;
+  int ldq, lds;   // leading dimensions of the element-major node / stage arrays
   int G, F, W, Hinv, gl, phi, psi, rb, dz, dzL, dzU, c, dlam;
   int crD, crU, crVL, crVU, crb, crx;
+  int lbr, ubr, rsl, rsu;
   int dynf, dynJ, dynH;   // NODE systems: per-node MLP dynamics values / Jacobians / contracted Hessians
   int ext;
   int total;
   MYR_HDI explicit Layout(const Problem& P) {
     Q = S::num_nodes(P); St = S::num_stages(P);
+    ldq = (Q + 3) & ~3;
+    lds = ((St + 3) & ~3) + 1;  // = 1 mod 4: the NC rows of a block (stride NC * lds doubles) fall into distinct shared-memory banks
     int o = 0;
-    G = o; o += Q * S::NC * S::NW;
-    F = o; o += Q * S::NC * S::NW;
-    W = o; o += Q * S::NWP;
-    Hinv = o; o += Q * S::NW * S::NW;
-    gl = o; o += Q * S::NW;
-    phi = o; o += Q * S::NC;
-    psi = o; o += Q * S::NC;
-    rb = o; o += Q * S::NW;
-    dz = o; o += Q * S::NW;
-    dzL = o; o += Q * S::NW;
-    dzU = o; o += Q * S::NW;
-    c = o; o += St * S::NC;
-    dlam = o; o += St * S::NC;
-    crD = o; o += St * S::NC * S::NC;
-    crU = o; o += St * S::NC * S::NC;
-    crVL = o; o += St * S::NC * S::NC;
-    crVU = o; o += St * S::NC * S::NC;
-    crb = o; o += St * S::NC;
+    G = o; o += ldq * S::NC * S::NW;
+    F = o; o += ldq * S::NC * S::NW;
+    W = o; o += ldq * S::NWP;
+    Hinv = o; o += ldq * S::NW * S::NW;
+    gl = o; o += ldq * S::NW;
+    phi = o; o += ldq * S::NC;
+    psi = o; o += ldq * S::NC;
+    rb = o; o += ldq * S::NW;
+    dz = o; o += ldq * S::NW;
+    dzL = o; o += ldq * S::NW;
+    dzU = o; o += ldq * S::NW;
+    c = o; o += lds * S::NC;
+    dlam = o; o += lds * S::NC;
+    crD = o; o += lds * S::NC * S::NC;
+    crU = o; o += lds * S::NC * S::NC;
+    crVL = o; o += lds * S::NC * S::NC;
+    crVU = o; o += lds * S::NC * S::NC;
+    crb = o; o += lds * S::NC;
     crx = dlam;  // CR writes its solution straight into dlam
+    lbr = o; o += ldq * S::NW;   // relaxed bounds per variable (-inf / +inf: none)
+    ubr = o; o += ldq * S::NW;
+    rsl = o; o += ldq * S::NW;   // reciprocal slacks 1 / (x - lbr), 1 / (ubr - x) of the current iterate
+    rsu = o; o += ldq * S::NW;
     dynf = dynJ = dynH = o;
     if (kCoopMlp) {
       dynf = o; o += Q * S::n;
@@ -78,8 +97,20 @@ struct Layout {
     total = (o + 15) & ~15;
   }
   // doubles of the CR scratch (D,U,VL,VU,b), contiguous from crD
-  MYR_HDI int cr_doubles() const { return St * (4 * S::NC * S::NC + S::NC); }
+  MYR_HDI int cr_doubles() const { return lds * (4 * S::NC * S::NC + S::NC); }
 };
+
+// Workspace arrays are element-major ("structure of arrays"): element e of node q lives at  base + e * ldq + q  (stage
+// arrays: base + e * lds + j), so the threads of a warp -- one node / stage each -- touch consecutive addresses.
+#define NQ(arr, q, e) w[L.arr + (e) * L.ldq + (q)]
+#define NS(arr, j, e) w[L.arr + (e) * L.lds + (j)]
+template <class T>
+struct Strided {
+  T* p; int s;
+  MYR_HDI T& operator[](int i) const { return p[(long long)i * s]; }
+};
+using SV = Strided<double>;
+using CSV = Strided<const double>;
 
 // ------------------------------------------------------------------ bounds helpers
 struct Bnd {
@@ -95,6 +126,19 @@ MYR_HDI Bnd make_bnd(double lb, double ub, double relax) {
   b.ubr = b.hasU ? ub + relax * fmax(1.0, fabs(ub)) : ub;
   return b;
 }
+
+// sum of log(slack) accumulated as log(product of slacks): one log per node instead of one per bound.  The product
+// is flushed whenever it leaves [1e-200, 1e200]; a non-positive slack poisons the result with NaN like log() would.
+struct LogProd {
+  double prod = 1.0, sum = 0.0;
+  bool bad = false;
+  MYR_HDI void mul(double s) {
+    bad = bad || !(s > 0.0);
+    prod *= s;
+    if (!(prod > 1e-200 && prod < 1e200)) { sum += log(prod); prod = 1.0; }
+  }
+  MYR_HDI double value() const { return bad ? NAN : sum + log(prod); }
+};
 
 // ------------------------------------------------------------------ K1: node evaluation sweep
 // Evaluates every node at point z (reference layout), stores node arrays in the workspace and returns the
@@ -129,16 +173,16 @@ MYR_HDI double eval_nodes(const Problem& P, const Layout<S>& L, const double* z,
     S::template eval_node<MODE>(P, q, v, lp, ls, ell, gl, phi, psi, G, F, W, pre);
     fsum += ell;
 #pragma unroll
-    for (int r = 0; r < S::NC; ++r) { w[L.phi + q * S::NC + r] = phi[r]; w[L.psi + q * S::NC + r] = psi[r]; }
+    for (int r = 0; r < S::NC; ++r) { NQ(phi, q, r) = phi[r]; NQ(psi, q, r) = psi[r]; }
     if (MODE >= 1) {
 #pragma unroll
-      for (int i = 0; i < S::NW; ++i) w[L.gl + q * S::NW + i] = gl[i];
+      for (int i = 0; i < S::NW; ++i) NQ(gl, q, i) = gl[i];
 #pragma unroll
-      for (int i = 0; i < S::NC * S::NW; ++i) { w[L.G + q * S::NC * S::NW + i] = G[i]; w[L.F + q * S::NC * S::NW + i] = F[i]; }
+      for (int i = 0; i < S::NC * S::NW; ++i) { NQ(G, q, i) = G[i]; NQ(F, q, i) = F[i]; }
     }
     if (MODE == 2) {
 #pragma unroll
-      for (int i = 0; i < S::NWP; ++i) w[L.W + q * S::NWP + i] = W[i];
+      for (int i = 0; i < S::NWP; ++i) NQ(W, q, i) = W[i];
     }
   }
   const double f = block_sum(fsum, red);
@@ -157,9 +201,9 @@ MYR_HDI void stage_constraints(const Problem& P, const Layout<S>& L, double* w, 
       double a = 0.0;
       for (int k = 0; k < nk; ++k) {
         int role; const int q = S::stage_node(P, j, k, role);
-        a += role ? w[L.psi + q * S::NC + r] : w[L.phi + q * S::NC + r];
+        a += role ? NQ(psi, q, r) : NQ(phi, q, r);
       }
-      cdst[j * S::NC + r] = a;
+      cdst[r * L.lds + j] = a;
       const double aa = (a != a) ? INFINITY : fabs(a);
       mx = fmax(mx, aa); sm += aa;
     }
@@ -171,8 +215,8 @@ MYR_HDI void stage_constraints(const Problem& P, const Layout<S>& L, double* w, 
 
 // ------------------------------------------------------------------ K2 pieces
 // small dense helpers on row-major blocks
-template <int R, int K, int C>
-MYR_HDI void mm(const double* A, const double* Bm, double* Cm) {  // C = A(RxK) B(KxC)
+template <int R, int K, int C, class TA, class TB>
+MYR_HDI void mm(const TA& A, const TB& Bm, double* Cm) {  // C = A(RxK) B(KxC)
 #pragma unroll
   for (int i = 0; i < R; ++i)
 #pragma unroll
@@ -183,187 +227,191 @@ MYR_HDI void mm(const double* A, const double* Bm, double* Cm) {  // C = A(RxK) 
       Cm[i * C + j] = s;
     }
 }
-template <int R, int K, int C>
-MYR_HDI void mm_nt_sub(const double* A, const double* Bm, double* Cm) {  // C -= A(RxK) B(CxK)^T
-#pragma unroll
-  for (int i = 0; i < R; ++i)
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < K; ++k) s += A[i * K + k] * Bm[j * K + k];
-      Cm[i * C + j] -= s;
-    }
-}
-
 // Block cyclic reduction for the symmetric block-tridiagonal system
 //   U_{i-1}^T x_{i-1} + D_i x_i + U_i x_{i+1} = b_i,   i = 0..St-1,  blocks NC x NC (D symmetric, may be indefinite).
 // Factor and solve are fused (single right-hand side).  Pivot-block inertias are accumulated: by Sylvester's
 // law their sum is the inertia of the whole matrix.  D,U,b are destroyed; x receives the solution.
+// All block arrays are element-major with leading dimension ld: entry k of block i is at  A[k * ld + i].
+//
+// Work decomposition: a GROUP of G = pow2 >= NC adjacent lanes owns one block; lane r of the group produces ROW r of
+// every block product of that block (the pivot-block inverse is computed redundantly by the lanes of the group: it is
+// a serial chain anyway).  With one thread per block the cost of a level does not shrink with the number of blocks
+// left, and the deep levels (13, 6, 3, 2, 1 blocks) dominate; with row-parallel groups a level costs roughly the
+// latency of one inverse plus a few row products.  On the host (one "thread") a group degenerates to a loop over rows.
 template <int NC>
-MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU, double* b, double* x,
+struct CrGroup { static constexpr int G = NC <= 1 ? 1 : (NC <= 2 ? 2 : (NC <= 4 ? 4 : (NC <= 8 ? 8 : 16))); };
+
+#ifdef __CUDA_ARCH__
+#define MYR_CR_ROWS(r) for (int r = int(threadIdx.x) % G; r < NC; r += G)
+#else
+#define MYR_CR_ROWS(r) for (int r = 0; r < NC; ++r)
+#endif
+
+template <int NC>
+MYR_HDI void block_cr_solve(int St, int ld, double* D, double* U, double* VL, double* VU, double* b, double* x,
                             double* red, int& npos, int& nneg, int& nzero) {
   constexpr int BB = NC * NC;
+  constexpr int G = CrGroup<NC>::G;
+#ifdef __CUDA_ARCH__
+  const int grp = int(threadIdx.x) / G, ngrp = int(blockDim.x) / G;
+  const bool counter = (int(threadIdx.x) % G) == 0;
+#else
+  const int grp = 0, ngrp = 1;
+  const bool counter = true;
+#endif
   int cp = 0, cn = 0, cz = 0;
-  int s = 1;
-  for (; s < St; s <<= 1) {
-    // eliminate odd multiples of s
-    for (int i = (2 * MYR_TID + 1) * s; i < St; i += 2 * MYR_NT * s) {
-      double A[BB], Dinv[BB];
+#if defined(MYR_PROFILE_PHASES) && defined(__CUDA_ARCH__)
+  long long cph_t0_ = clock64();
+#define MYR_CPH(idx) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase_cycles[idx], (unsigned long long)(t_ - cph_t0_)); cph_t0_ = t_; } } while (0)
+#else
+#define MYR_CPH(idx) do { } while (0)
+#endif
+  // pivot inverse of block i (symmetrised on load), row r selected into dr without dynamic register indexing
+  auto pivot_rows = [&](int i, double* Dinv) {
+    double A[BB];
 #pragma unroll
-      for (int k = 0; k < BB; ++k) A[k] = D[i * BB + k];
-      int p_, n_, z_;
-      sym_inverse<NC>(A, 0u, Dinv, p_, n_, z_);
-      cp += p_; cn += n_; cz += z_;
-      // VL = Dinv * U_{i-s}^T
-      const double* Ul = U + (i - s) * BB;
-      double T[BB];
+    for (int r = 0; r < NC; ++r)
 #pragma unroll
-      for (int r = 0; r < NC; ++r)
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          double a = 0.0;
-#pragma unroll
-          for (int k = 0; k < NC; ++k) a += Dinv[r * NC + k] * Ul[c * NC + k];
-          T[r * NC + c] = a;
-        }
-#pragma unroll
-      for (int k = 0; k < BB; ++k) VL[i * BB + k] = T[k];
-      if (i + s < St) {
-        mm<NC, NC, NC>(Dinv, U + i * BB, T);
-#pragma unroll
-        for (int k = 0; k < BB; ++k) VU[i * BB + k] = T[k];
-      }
-      double vb[NC];
-#pragma unroll
-      for (int r = 0; r < NC; ++r) {
-        double a = 0.0;
-#pragma unroll
-        for (int k = 0; k < NC; ++k) a += Dinv[r * NC + k] * b[i * NC + k];
-        vb[r] = a;
-      }
-#pragma unroll
-      for (int r = 0; r < NC; ++r) b[i * NC + r] = vb[r];
-#pragma unroll
-      for (int k = 0; k < BB; ++k) D[i * BB + k] = Dinv[k];  // keep the pivot inverse for later re-solves
-    }
-    MYR_SYNC();
-    // update even multiples of s
-    for (int i = 2 * MYR_TID * s; i < St; i += 2 * MYR_NT * s) {
-      double Dn[BB], bn[NC], Un[BB];
-#pragma unroll
-      for (int k = 0; k < BB; ++k) { Dn[k] = D[i * BB + k]; Un[k] = 0.0; }
-#pragma unroll
-      for (int r = 0; r < NC; ++r) bn[r] = b[i * NC + r];
-      const int er = i + s;
-      if (er < St) {
-        const double* Ui = U + i * BB;
-        const double* vl = VL + er * BB;
-#pragma unroll
-        for (int r = 0; r < NC; ++r) {
-#pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            double a = 0.0;
-#pragma unroll
-            for (int k = 0; k < NC; ++k) a += Ui[r * NC + k] * vl[k * NC + c];
-            Dn[r * NC + c] -= a;
-          }
-          double a = 0.0;
-#pragma unroll
-          for (int k = 0; k < NC; ++k) a += Ui[r * NC + k] * b[er * NC + k];
-          bn[r] -= a;
-        }
-        if (er + s < St) {
-          const double* vu = VU + er * BB;
-#pragma unroll
-          for (int r = 0; r < NC; ++r)
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-              double a = 0.0;
-#pragma unroll
-              for (int k = 0; k < NC; ++k) a += Ui[r * NC + k] * vu[k * NC + c];
-              Un[r * NC + c] = -a;
-            }
-        }
-      }
-      const int el = i - s;
-      if (el >= 0) {
-        const double* Ue = U + el * BB;     // coupling el -> i  (row el, col i); we need Ue^T
-        const double* vu = VU + el * BB;
-#pragma unroll
-        for (int r = 0; r < NC; ++r) {
-#pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            double a = 0.0;
-#pragma unroll
-            for (int k = 0; k < NC; ++k) a += Ue[k * NC + r] * vu[k * NC + c];
-            Dn[r * NC + c] -= a;
-          }
-          double a = 0.0;
-#pragma unroll
-          for (int k = 0; k < NC; ++k) a += Ue[k * NC + r] * b[el * NC + k];
-          bn[r] -= a;
-        }
-      }
-      // symmetrise D (rounding) and store
-#pragma unroll
-      for (int r = 0; r < NC; ++r)
-#pragma unroll
-        for (int c = 0; c < NC; ++c) D[i * BB + r * NC + c] = 0.5 * (Dn[r * NC + c] + Dn[c * NC + r]);
-#pragma unroll
-      for (int k = 0; k < BB; ++k) U[i * BB + k] = Un[k];
-#pragma unroll
-      for (int r = 0; r < NC; ++r) b[i * NC + r] = bn[r];
-    }
-    MYR_SYNC();
-  }
-  // root
-  if (MYR_TID == 0) {
-    double A[BB], Dinv[BB];
-#pragma unroll
-    for (int k = 0; k < BB; ++k) A[k] = D[k];
+      for (int c = 0; c < NC; ++c) A[r * NC + c] = 0.5 * (D[(r * NC + c) * ld + i] + D[(c * NC + r) * ld + i]);
     int p_, n_, z_;
     sym_inverse<NC>(A, 0u, Dinv, p_, n_, z_);
-    cp += p_; cn += n_; cz += z_;
+    if (counter) { cp += p_; cn += n_; cz += z_; }
+  };
+  int s = 1;
+  for (; s < St; s <<= 1) {
+    const int nodd = (St - s + 2 * s - 1) / (2 * s);   // blocks i = (2k+1) s < St
+    const int neven = (St + 2 * s - 1) / (2 * s);      // blocks i = 2k s < St
+    // ---- eliminate the odd blocks: Dinv_i (kept in D), VL_i = Dinv_i U_{i-s}^T, VU_i = Dinv_i U_i, x_i = Dinv_i b_i
+    for (int k0 = 0; k0 < nodd; k0 += ngrp) {   // trip count uniform across the CTA (the loop contains a warp barrier)
+      const int k = k0 + grp;
+      const bool active = k < nodd;
+      const int i = active ? (2 * k + 1) * s : s;
+      double Dinv[BB], Ul[BB], Ui[BB], bi[NC];
+      const bool hr = i + s < St;
+      if (active) {
+        pivot_rows(i, Dinv);
 #pragma unroll
-    for (int r = 0; r < NC; ++r) {
-      double a = 0.0;
+        for (int e = 0; e < BB; ++e) { Ul[e] = U[e * ld + (i - s)]; Ui[e] = hr ? U[e * ld + i] : 0.0; }
 #pragma unroll
-      for (int k = 0; k < NC; ++k) a += Dinv[r * NC + k] * b[k];
-      x[r] = a;
-    }
-#pragma unroll
-    for (int k = 0; k < BB; ++k) D[k] = Dinv[k];
-  }
-  MYR_SYNC();
-  // back substitution
-  for (s >>= 1; s >= 1; s >>= 1) {
-    for (int i = (2 * MYR_TID + 1) * s; i < St; i += 2 * MYR_NT * s) {
-      double xi[NC];
-#pragma unroll
-      for (int r = 0; r < NC; ++r) xi[r] = b[i * NC + r];
-      const double* vl = VL + i * BB;
-      const double* xl = x + (i - s) * NC;
-#pragma unroll
-      for (int r = 0; r < NC; ++r) {
-        double a = 0.0;
-#pragma unroll
-        for (int k = 0; k < NC; ++k) a += vl[r * NC + k] * xl[k];
-        xi[r] -= a;
+        for (int m = 0; m < NC; ++m) bi[m] = b[m * ld + i];
       }
-      if (i + s < St) {
-        const double* vu = VU + i * BB;
-        const double* xr = x + (i + s) * NC;
+#ifdef __CUDA_ARCH__
+      __syncwarp();  // every lane of the group has read D_i before rows of it are overwritten
+#endif
+      if (active) {
+        MYR_CR_ROWS(r) {
+          double dr[NC];
 #pragma unroll
-        for (int r = 0; r < NC; ++r) {
-          double a = 0.0;
+          for (int m = 0; m < NC; ++m) {
+            double v = 0.0;
 #pragma unroll
-          for (int k = 0; k < NC; ++k) a += vu[r * NC + k] * xr[k];
-          xi[r] -= a;
+            for (int rr = 0; rr < NC; ++rr) v = (rr == r) ? Dinv[rr * NC + m] : v;
+            dr[m] = v;
+          }
+          double xr = 0.0;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            double vl = 0.0, vu = 0.0;
+#pragma unroll
+            for (int m = 0; m < NC; ++m) { vl += dr[m] * Ul[c * NC + m]; vu += dr[m] * Ui[m * NC + c]; }
+            VL[(r * NC + c) * ld + i] = vl;
+            if (hr) VU[(r * NC + c) * ld + i] = vu;
+            D[(r * NC + c) * ld + i] = dr[c];
+            xr += dr[c] * bi[c];
+          }
+          x[r * ld + i] = xr;
         }
       }
+    }
+    MYR_SYNC();
+    MYR_CPH(s == 1 ? 10 : (s == 2 ? 12 : 14));
+    // ---- update the even blocks i from their eliminated neighbours er = i + s, el = i - s (row r per lane, in place)
+    for (int k = grp; k < neven; k += ngrp) {
+      const int i = 2 * k * s, er = i + s, el = i - s;
+      const bool hr = er < St, hl = el >= 0, hrr = hr && er + s < St;
+      MYR_CR_ROWS(r) {
+        double dn[NC], un[NC], ur[NC], uc[NC];
+        double bn = b[r * ld + i];
 #pragma unroll
-      for (int r = 0; r < NC; ++r) x[i * NC + r] = xi[r];
+        for (int c = 0; c < NC; ++c) {
+          dn[c] = D[(r * NC + c) * ld + i]; un[c] = 0.0;
+          ur[c] = hr ? U[(r * NC + c) * ld + i] : 0.0;      // row r of U_i
+          uc[c] = hl ? U[(c * NC + r) * ld + el] : 0.0;     // column r of U_el = row r of U_el^T
+        }
+        if (hr) {
+#pragma unroll
+          for (int m = 0; m < NC; ++m) {
+            const double u_ = ur[m];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) dn[c] -= u_ * VL[(m * NC + c) * ld + er];
+            bn -= u_ * x[m * ld + er];
+          }
+          if (hrr) {
+#pragma unroll
+            for (int m = 0; m < NC; ++m) {
+              const double u_ = ur[m];
+#pragma unroll
+              for (int c = 0; c < NC; ++c) un[c] -= u_ * VU[(m * NC + c) * ld + er];
+            }
+          }
+        }
+        if (hl) {
+#pragma unroll
+          for (int m = 0; m < NC; ++m) {
+            const double u_ = uc[m];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) dn[c] -= u_ * VU[(m * NC + c) * ld + el];
+            bn -= u_ * x[m * ld + el];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { D[(r * NC + c) * ld + i] = dn[c]; U[(r * NC + c) * ld + i] = un[c]; }
+        b[r * ld + i] = bn;
+      }
+    }
+    MYR_SYNC();
+    MYR_CPH(s == 1 ? 11 : (s == 2 ? 13 : 15));
+  }
+  // ---- root (block 0): loads and inverse, CTA barrier, then the rows (the barrier separates reads of D_0 from writes)
+  {
+    double Dinv[BB], bi[NC];
+    if (grp == 0) {
+      pivot_rows(0, Dinv);
+#pragma unroll
+      for (int m = 0; m < NC; ++m) bi[m] = b[m * ld];
+    }
+    MYR_SYNC();
+    if (grp == 0) {
+      MYR_CR_ROWS(r) {
+        double xr = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          double v = 0.0;
+#pragma unroll
+          for (int rr = 0; rr < NC; ++rr) v = (rr == r) ? Dinv[rr * NC + c] : v;
+          D[(r * NC + c) * ld] = v;
+          xr += v * bi[c];
+        }
+        x[r * ld] = xr;
+      }
+    }
+  }
+  MYR_SYNC();
+  // ---- back substitution: x_i = (Dinv_i b_i) - VL_i x_{i-s} - VU_i x_{i+s}
+  for (s >>= 1; s >= 1; s >>= 1) {
+    const int nodd = (St - s + 2 * s - 1) / (2 * s);
+    for (int k = grp; k < nodd; k += ngrp) {
+      const int i = (2 * k + 1) * s;
+      MYR_CR_ROWS(r) {
+        double a = x[r * ld + i];
+#pragma unroll
+        for (int m = 0; m < NC; ++m) a -= VL[(r * NC + m) * ld + i] * x[m * ld + (i - s)];
+        if (i + s < St) {
+#pragma unroll
+          for (int m = 0; m < NC; ++m) a -= VU[(r * NC + m) * ld + i] * x[m * ld + (i + s)];
+        }
+        x[r * ld + i] = a;
+      }
     }
     MYR_SYNC();
   }
@@ -378,37 +426,34 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
 // the elimination of e from its surviving neighbours is  b_i -= VL_e^T b_e  (right neighbour e = i+s) and
 // b_i -= VU_e^T b_e (left neighbour e = i-s), which only needs data of already-final eliminated nodes.
 template <int NC>
-MYR_HDI void block_cr_resolve(int St, const double* D, const double* VL, const double* VU, double* b, double* x) {
-  constexpr int BB = NC * NC;
+MYR_HDI void block_cr_resolve(int St, int ld, const double* D, const double* VL, const double* VU, double* b, double* x) {
   int s = 1;
   for (; s < St; s <<= 1) {
     for (int i = 2 * MYR_TID * s; i < St; i += 2 * MYR_NT * s) {
       double bn[NC];
 #pragma unroll
-      for (int r = 0; r < NC; ++r) bn[r] = b[i * NC + r];
+      for (int r = 0; r < NC; ++r) bn[r] = b[r * ld + i];
       const int er = i + s, el = i - s;
       if (er < St) {
-        const double* vl = VL + er * BB;
 #pragma unroll
         for (int r = 0; r < NC; ++r) {
           double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < NC; ++k) a += vl[k * NC + r] * b[er * NC + k];
+          for (int k = 0; k < NC; ++k) a += VL[(k * NC + r) * ld + er] * b[k * ld + er];
           bn[r] -= a;
         }
       }
       if (el >= 0) {
-        const double* vu = VU + el * BB;
 #pragma unroll
         for (int r = 0; r < NC; ++r) {
           double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < NC; ++k) a += vu[k * NC + r] * b[el * NC + k];
+          for (int k = 0; k < NC; ++k) a += VU[(k * NC + r) * ld + el] * b[k * ld + el];
           bn[r] -= a;
         }
       }
 #pragma unroll
-      for (int r = 0; r < NC; ++r) b[i * NC + r] = bn[r];
+      for (int r = 0; r < NC; ++r) b[r * ld + i] = bn[r];
     }
     MYR_SYNC();
   }
@@ -417,44 +462,39 @@ MYR_HDI void block_cr_resolve(int St, const double* D, const double* VL, const d
     for (int r = 0; r < NC; ++r) {
       double a = 0.0;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) a += D[r * NC + k] * b[k];
-      x[r] = a;
+      for (int k = 0; k < NC; ++k) a += D[(r * NC + k) * ld] * b[k * ld];
+      x[r * ld] = a;
     }
   }
   MYR_SYNC();
   for (s >>= 1; s >= 1; s >>= 1) {
     for (int i = (2 * MYR_TID + 1) * s; i < St; i += 2 * MYR_NT * s) {
       double xi[NC];
-      const double* di = D + i * BB;
 #pragma unroll
       for (int r = 0; r < NC; ++r) {
         double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) a += di[r * NC + k] * b[i * NC + k];
+        for (int k = 0; k < NC; ++k) a += D[(r * NC + k) * ld + i] * b[k * ld + i];
         xi[r] = a;
       }
-      const double* vl = VL + i * BB;
-      const double* xl = x + (i - s) * NC;
 #pragma unroll
       for (int r = 0; r < NC; ++r) {
         double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) a += vl[r * NC + k] * xl[k];
+        for (int k = 0; k < NC; ++k) a += VL[(r * NC + k) * ld + i] * x[k * ld + (i - s)];
         xi[r] -= a;
       }
       if (i + s < St) {
-        const double* vu = VU + i * BB;
-        const double* xr = x + (i + s) * NC;
 #pragma unroll
         for (int r = 0; r < NC; ++r) {
           double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < NC; ++k) a += vu[r * NC + k] * xr[k];
+          for (int k = 0; k < NC; ++k) a += VU[(r * NC + k) * ld + i] * x[k * ld + (i + s)];
           xi[r] -= a;
         }
       }
 #pragma unroll
-      for (int r = 0; r < NC; ++r) x[i * NC + r] = xi[r];
+      for (int r = 0; r < NC; ++r) x[r * ld + i] = xi[r];
     }
     MYR_SYNC();
   }
@@ -471,12 +511,18 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
                        double delta_reg = 0.0, int max_refine = 0) {
   constexpr int NW = S::NW, NC = S::NC;
   const int Q = L.Q, St = L.St;
+#if defined(MYR_PROFILE_PHASES) && defined(__CUDA_ARCH__)
+  long long kph_t0_ = clock64();
+#define MYR_KPH(idx) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase_cycles[idx], (unsigned long long)(t_ - kph_t0_)); kph_t0_ = t_; } } while (0)
+#else
+#define MYR_KPH(idx) do { } while (0)
+#endif
   // ---- node blocks: Hinv = (W + Sigma + dw)^-1 with fixed variables removed; inertia of H
   int hp = 0, hn = 0, hz = 0;
   double minpr = INFINITY;
   for (int q = MYR_TID; q < Q; q += MYR_NT) {
     double A[NW * NW], inv[NW * NW];
-    const double* Wq = w + L.W + q * S::NWP;
+    const CSV Wq{w + L.W + q, L.ldq};
 #pragma unroll
     for (int i = 0; i < NW; ++i)
 #pragma unroll
@@ -489,7 +535,7 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
     minpr = fmin(minpr, pr_);
     hp += p_; hn += n_; hz += z_;
 #pragma unroll
-    for (int i = 0; i < NW * NW; ++i) w[L.Hinv + q * NW * NW + i] = inv[i];
+    for (int i = 0; i < NW * NW; ++i) NQ(Hinv, q, i) = inv[i];
   }
   const int Hneg = (int)(block_sum((double)hn, red) + 0.5);
   const int Hzero = (int)(block_sum((double)hz, red) + 0.5);
@@ -498,21 +544,29 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
   if (!(minpr < 1e-4)) max_refine = 0;
   (void)hp;
   MYR_SYNC();
+  MYR_KPH(6);
   // ---- stage blocks of the Schur complement S = J Hinv J^T + dc I and its right-hand side  c - J Hinv rb
-  double* D = cr; double* U = D + St * NC * NC; double* VL = U + St * NC * NC; double* VU = VL + St * NC * NC;
-  double* bb = VU + St * NC * NC;
+  const int ld = L.lds;
+  double* D = cr; double* U = D + ld * NC * NC; double* VL = U + ld * NC * NC; double* VU = VL + ld * NC * NC;
+  double* bb = VU + ld * NC * NC;
   for (int j = MYR_TID; j < St; j += MYR_NT) {
     double Dj[NC * NC], bj[NC];
 #pragma unroll
     for (int i = 0; i < NC * NC; ++i) Dj[i] = 0.0;
 #pragma unroll
-    for (int r = 0; r < NC; ++r) { Dj[r * NC + r] = delta_c; bj[r] = w[L.c + j * NC + r]; }
+    for (int r = 0; r < NC; ++r) { Dj[r * NC + r] = delta_c; bj[r] = NS(c, j, r); }
     const int nk = S::stage_nodes(P, j);
     for (int k = 0; k < nk; ++k) {
       int role; const int q = S::stage_node(P, j, k, role);
-      const double* Jq = w + (role ? L.F : L.G) + q * NC * NW;
-      const double* Hi = w + L.Hinv + q * NW * NW;
-      double T[NC * NW];
+      double Jq[NC * NW], Hi[NW * NW], T[NC * NW];
+      {
+        const CSV Jv{w + (role ? L.F : L.G) + q, L.ldq};
+        const CSV Hv{w + L.Hinv + q, L.ldq};
+#pragma unroll
+        for (int i = 0; i < NC * NW; ++i) Jq[i] = Jv[i];
+#pragma unroll
+        for (int i = 0; i < NW * NW; ++i) Hi[i] = Hv[i];
+      }
       mm<NC, NW, NW>(Jq, Hi, T);
 #pragma unroll
       for (int r = 0; r < NC; ++r) {
@@ -525,11 +579,11 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
         }
         double a = 0.0;
 #pragma unroll
-        for (int i = 0; i < NW; ++i) a += T[r * NW + i] * w[L.rb + q * NW + i];
+        for (int i = 0; i < NW; ++i) a += T[r * NW + i] * NQ(rb, q, i);
         bj[r] -= a;
       }
       if (role == 1 && j + 1 < St) {  // link node: coupling to the next stage  U_j = F Hinv G^T
-        const double* Gq = w + L.G + q * NC * NW;
+        const CSV Gq{w + L.G + q, L.ldq};
 #pragma unroll
         for (int r = 0; r < NC; ++r)
 #pragma unroll
@@ -537,53 +591,55 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
             double a = 0.0;
 #pragma unroll
             for (int i = 0; i < NW; ++i) a += T[r * NW + i] * Gq[c2 * NW + i];
-            U[j * NC * NC + r * NC + c2] = a;
+            U[(r * NC + c2) * ld + j] = a;
           }
       }
     }
 #pragma unroll
     for (int r = 0; r < NC; ++r)
 #pragma unroll
-      for (int c2 = 0; c2 < NC; ++c2) D[j * NC * NC + r * NC + c2] = 0.5 * (Dj[r * NC + c2] + Dj[c2 * NC + r]);
+      for (int c2 = 0; c2 < NC; ++c2) D[(r * NC + c2) * ld + j] = 0.5 * (Dj[r * NC + c2] + Dj[c2 * NC + r]);
 #pragma unroll
-    for (int r = 0; r < NC; ++r) bb[j * NC + r] = bj[r];
+    for (int r = 0; r < NC; ++r) bb[r * ld + j] = bj[r];
   }
   MYR_SYNC();
+  MYR_KPH(7);
   int sp, sn, sz;
-  block_cr_solve<NC>(St, D, U, VL, VU, bb, w + L.dlam, red, sp, sn, sz);
+  block_cr_solve<NC>(St, ld, D, U, VL, VU, bb, w + L.dlam, red, sp, sn, sz);
+  MYR_KPH(8);
   // inertia(K) = inertia(H) + inertia(-S): correct iff  n-(S) == n-(H)  and nothing is singular
   const bool ok = (Hzero == 0) && (sz == 0) && (sn == Hneg);
   // ---- dz = -Hinv (rb + G^T dlam_phi + F^T dlam_psi)
   for (int q = MYR_TID; q < Q; q += MYR_NT) {
     double v[NW];
 #pragma unroll
-    for (int i = 0; i < NW; ++i) v[i] = w[L.rb + q * NW + i];
+    for (int i = 0; i < NW; ++i) v[i] = NQ(rb, q, i);
     const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
     if (jp >= 0) {
-      const double* Gq = w + L.G + q * NC * NW;
+      const CSV Gq{w + L.G + q, L.ldq};
 #pragma unroll
       for (int r = 0; r < NC; ++r) {
-        const double d = w[L.dlam + jp * NC + r];
+        const double d = NS(dlam, jp, r);
 #pragma unroll
         for (int i = 0; i < NW; ++i) v[i] += Gq[r * NW + i] * d;
       }
     }
     if (js >= 0) {
-      const double* Fq = w + L.F + q * NC * NW;
+      const CSV Fq{w + L.F + q, L.ldq};
 #pragma unroll
       for (int r = 0; r < NC; ++r) {
-        const double d = w[L.dlam + js * NC + r];
+        const double d = NS(dlam, js, r);
 #pragma unroll
         for (int i = 0; i < NW; ++i) v[i] += Fq[r * NW + i] * d;
       }
     }
-    const double* Hi = w + L.Hinv + q * NW * NW;
+    const CSV Hi{w + L.Hinv + q, L.ldq};
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
       double a = 0.0;
 #pragma unroll
       for (int k = 0; k < NW; ++k) a += Hi[i * NW + k] * v[k];
-      w[L.dz + q * NW + i] = -a;
+      NQ(dz, q, i) = -a;
     }
   }
   MYR_SYNC();
@@ -597,8 +653,8 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
     for (int q = MYR_TID; q < Q; q += MYR_NT) {
       double v[NW], d[NW];
 #pragma unroll
-      for (int i = 0; i < NW; ++i) { v[i] = -w[L.rb + q * NW + i]; d[i] = w[L.dz + q * NW + i]; smax = fmax(smax, fabs(v[i])); }
-      const double* Wq = w + L.W + q * S::NWP;
+      for (int i = 0; i < NW; ++i) { v[i] = -NQ(rb, q, i); d[i] = NQ(dz, q, i); smax = fmax(smax, fabs(v[i])); }
+      const CSV Wq{w + L.W + q, L.ldq};
 #pragma unroll
       for (int i = 0; i < NW; ++i) {
         double a = (sigma[q * NW + i] + delta_w) * d[i];
@@ -608,19 +664,19 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
       }
       const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
       if (jp >= 0) {
-        const double* Gq = w + L.G + q * NC * NW;
+        const CSV Gq{w + L.G + q, L.ldq};
 #pragma unroll
         for (int r = 0; r < NC; ++r) {
-          const double dl = w[L.dlam + jp * NC + r];
+          const double dl = NS(dlam, jp, r);
 #pragma unroll
           for (int i = 0; i < NW; ++i) v[i] -= Gq[r * NW + i] * dl;
         }
       }
       if (js >= 0) {
-        const double* Fq = w + L.F + q * NC * NW;
+        const CSV Fq{w + L.F + q, L.ldq};
 #pragma unroll
         for (int r = 0; r < NC; ++r) {
-          const double dl = w[L.dlam + js * NC + r];
+          const double dl = NS(dlam, js, r);
 #pragma unroll
           for (int i = 0; i < NW; ++i) v[i] -= Fq[r * NW + i] * dl;
         }
@@ -629,7 +685,7 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
       for (int i = 0; i < NW; ++i) {
         const bool fx = (fixmask[q] >> i) & 1u;
         const double r_ = fx ? 0.0 : v[i];
-        w[L.dzL + q * NW + i] = r_;
+        NQ(dzL, q, i) = r_;
         rmax = fmax(rmax, (r_ != r_) ? INFINITY : fabs(r_));
       }
     }
@@ -638,72 +694,72 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
     for (int j = MYR_TID; j < St; j += MYR_NT) {
       double rc[NC], bj[NC];
 #pragma unroll
-      for (int r = 0; r < NC; ++r) { rc[r] = -w[L.c + j * NC + r] + delta_c * w[L.dlam + j * NC + r]; bj[r] = 0.0; smax = fmax(smax, fabs(w[L.c + j * NC + r])); }
+      for (int r = 0; r < NC; ++r) { rc[r] = -NS(c, j, r) + delta_c * NS(dlam, j, r); bj[r] = 0.0; smax = fmax(smax, fabs(NS(c, j, r))); }
       const int nk = S::stage_nodes(P, j);
       for (int k = 0; k < nk; ++k) {
         int role; const int q = S::stage_node(P, j, k, role);
-        const double* Jq = w + (role ? L.F : L.G) + q * NC * NW;
-        const double* Hi = w + L.Hinv + q * NW * NW;
+        const CSV Jq{w + (role ? L.F : L.G) + q, L.ldq};
+        const CSV Hi{w + L.Hinv + q, L.ldq};
         double t[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
           double a = 0.0;
 #pragma unroll
-          for (int k2 = 0; k2 < NW; ++k2) a += Hi[i * NW + k2] * w[L.dzL + q * NW + k2];
+          for (int k2 = 0; k2 < NW; ++k2) a += Hi[i * NW + k2] * NQ(dzL, q, k2);
           t[i] = a;
         }
 #pragma unroll
         for (int r = 0; r < NC; ++r) {
           double a = 0.0, b_ = 0.0;
 #pragma unroll
-          for (int i = 0; i < NW; ++i) { a += Jq[r * NW + i] * w[L.dz + q * NW + i]; b_ += Jq[r * NW + i] * t[i]; }
+          for (int i = 0; i < NW; ++i) { a += Jq[r * NW + i] * NQ(dz, q, i); b_ += Jq[r * NW + i] * t[i]; }
           rc[r] -= a; bj[r] += b_;
         }
       }
 #pragma unroll
       for (int r = 0; r < NC; ++r) {
         rmax = fmax(rmax, (rc[r] != rc[r]) ? INFINITY : fabs(rc[r]));
-        bb[j * NC + r] = bj[r] - rc[r];
+        bb[r * ld + j] = bj[r] - rc[r];
       }
     }
     rmax = block_max(rmax, red);
     smax = block_max(smax, red);
     MYR_SYNC();
     if (!(rmax > 1e-13 * fmax(1.0, smax)) || !isfinite(rmax)) break;
-    block_cr_resolve<NC>(St, D, VL, VU, bb, w + L.dzU /* ddlam: St*NC <= Q*NW */);
+    block_cr_resolve<NC>(St, ld, D, VL, VU, bb, w + L.dzU /* ddlam: lds*NC <= ldq*NW */);
     for (int j = MYR_TID; j < St; j += MYR_NT)
 #pragma unroll
-      for (int r = 0; r < NC; ++r) w[L.dlam + j * NC + r] += w[L.dzU + j * NC + r];
+      for (int r = 0; r < NC; ++r) NS(dlam, j, r) += NS(dzU, j, r);
     for (int q = MYR_TID; q < Q; q += MYR_NT) {
       double v[NW];
 #pragma unroll
-      for (int i = 0; i < NW; ++i) v[i] = w[L.dzL + q * NW + i];
+      for (int i = 0; i < NW; ++i) v[i] = NQ(dzL, q, i);
       const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
       if (jp >= 0) {
-        const double* Gq = w + L.G + q * NC * NW;
+        const CSV Gq{w + L.G + q, L.ldq};
 #pragma unroll
         for (int r = 0; r < NC; ++r) {
-          const double d = w[L.dzU + jp * NC + r];
+          const double d = NS(dzU, jp, r);
 #pragma unroll
           for (int i = 0; i < NW; ++i) v[i] -= Gq[r * NW + i] * d;
         }
       }
       if (js >= 0) {
-        const double* Fq = w + L.F + q * NC * NW;
+        const CSV Fq{w + L.F + q, L.ldq};
 #pragma unroll
         for (int r = 0; r < NC; ++r) {
-          const double d = w[L.dzU + js * NC + r];
+          const double d = NS(dzU, js, r);
 #pragma unroll
           for (int i = 0; i < NW; ++i) v[i] -= Fq[r * NW + i] * d;
         }
       }
-      const double* Hi = w + L.Hinv + q * NW * NW;
+      const CSV Hi{w + L.Hinv + q, L.ldq};
 #pragma unroll
       for (int i = 0; i < NW; ++i) {
         double a = 0.0;
 #pragma unroll
         for (int k = 0; k < NW; ++k) a += Hi[i * NW + k] * v[k];
-        w[L.dz + q * NW + i] += a;
+        NQ(dz, q, i) += a;
       }
     }
     MYR_SYNC();
@@ -779,60 +835,61 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       z[id] = x;
       zL[id] = bd.hasL ? 1.0 : 0.0;
       zU[id] = bd.hasU ? 1.0 : 0.0;
+      NQ(lbr, q, i) = bd.fixed ? lb[id] : (bd.hasL ? bd.lbr : -INFINITY);
+      NQ(ubr, q, i) = bd.fixed ? lb[id] : (bd.hasU ? bd.ubr : INFINITY);
     }
     fix_sh[q] = fm;
   }
   for (int k = MYR_TID; k < ncn; k += MYR_NT) lam[k] = 0.0;
   MYR_SYNC();
 
+  MYR_PH_DECL
   double mu = O.mu_init, nu = 1.0, delta_last = 0.0;
+#ifdef MYR_COUNT_KKT
+  int n_kkt = 0;
+#endif
   int it = 0, status = ST_MAXITER, n_acceptable = 0;
   double f = 0.0, E0 = INFINITY, cinf = INFINITY, c1 = 0.0;
   const double mu_floor = fmax(O.mu_min, O.tol / 10.0);
 
   while (true) {
     // ---------------- K1: evaluate with derivatives
+    MYR_PH(9);
     f = eval_nodes<S, 2>(P, L, z, lam, w, red, mlp_scr);
     stage_constraints<S>(P, L, w, w + L.c, red, cinf, c1);
+    MYR_PH(0);
     // ---------------- dual residual, complementarity, scaling sums
+    // (per-variable loops are deliberately NOT unrolled: the body is long and the kernel is instruction-fetch bound)
     double rdmax = 0.0, szmax = -INFINITY, szmin = INFINITY, sumz = 0.0, nbnd = 0.0, slog = 0.0;
     for (int q = MYR_TID; q < Q; q += MYR_NT) {
       const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-      const double* Gq = w + L.G + q * NC * NW;
-      const double* Fq = w + L.F + q * NC * NW;
-      double r[NW];
+      double lp[NC], ls[NC];
 #pragma unroll
-      for (int i = 0; i < NW; ++i) r[i] = w[L.gl + q * NW + i];
-      if (jp >= 0) {
-#pragma unroll
-        for (int rr = 0; rr < NC; ++rr) {
-          const double l = lam[S::cidx(P, jp, rr)];
-#pragma unroll
-          for (int i = 0; i < NW; ++i) r[i] += Gq[rr * NW + i] * l;
-        }
+      for (int rr = 0; rr < NC; ++rr) {
+        lp[rr] = jp >= 0 ? lam[S::cidx(P, jp, rr)] : 0.0;
+        ls[rr] = js >= 0 ? lam[S::cidx(P, js, rr)] : 0.0;
       }
-      if (js >= 0) {
-#pragma unroll
-        for (int rr = 0; rr < NC; ++rr) {
-          const double l = lam[S::cidx(P, js, rr)];
-#pragma unroll
-          for (int i = 0; i < NW; ++i) r[i] += Fq[rr * NW + i] * l;
-        }
-      }
-#pragma unroll
+      const uint32_t fm = fix_sh[q];
+      LogProd lpq;
+#pragma unroll 1
       for (int i = 0; i < NW; ++i) {
         const int id = S::zidx(P, q, i);
-        const Bnd bd = make_bnd(lb[id], ub[id], O.bound_relax);
+        double r = NQ(gl, q, i);
+#pragma unroll
+        for (int rr = 0; rr < NC; ++rr) r += NQ(G, q, rr * NW + i) * lp[rr] + NQ(F, q, rr * NW + i) * ls[rr];
+        const bool fixed = (fm >> i) & 1u;
         double rd = 0.0;
-        if (!bd.fixed) {
-          rd = r[i] - zL[id] + zU[id];
-          if (bd.hasL) { const double sl = z[id] - bd.lbr; const double pz = sl * zL[id]; szmax = fmax(szmax, pz); szmin = fmin(szmin, pz); sumz += zL[id]; nbnd += 1.0; slog += log(sl); }
-          if (bd.hasU) { const double su = bd.ubr - z[id]; const double pz = su * zU[id]; szmax = fmax(szmax, pz); szmin = fmin(szmin, pz); sumz += zU[id]; nbnd += 1.0; slog += log(su); }
+        if (!fixed) {
+          const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = z[id], zl = zL[id], zu = zU[id];
+          rd = r - zl + zu;
+          if (lo > -INFINITY) { const double sl = x - lo; const double pz = sl * zl; szmax = fmax(szmax, pz); szmin = fmin(szmin, pz); sumz += zl; nbnd += 1.0; lpq.mul(sl); }
+          if (hi < INFINITY) { const double su = hi - x; const double pz = su * zu; szmax = fmax(szmax, pz); szmin = fmin(szmin, pz); sumz += zu; nbnd += 1.0; lpq.mul(su); }
         }
-        w[L.rb + q * NW + i] = bd.fixed ? 0.0 : r[i];  // grad f + J^T lam (barrier terms added after mu is known)
+        NQ(rb, q, i) = fixed ? 0.0 : r;  // grad f + J^T lam (barrier terms added after mu is known)
         const double a = (rd != rd) ? INFINITY : fabs(rd);
         rdmax = fmax(rdmax, a);
       }
+      slog += lpq.value();
     }
     double suml = 0.0;
     for (int k = MYR_TID; k < ncn; k += MYR_NT) suml += fabs(lam[k]);
@@ -860,27 +917,35 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     while (mu > mu_floor && Emu(mu) <= O.kappa_eps * mu) mu = fmax(mu_floor, fmin(O.kappa_mu * mu, pow(mu, O.theta_mu)));
     const double tau = fmax(O.tau_min, 1.0 - mu);
 
-    // ---------------- barrier gradient rb and Sigma
-    double dphi_lin = 0.0;
+    MYR_PH(1);
+    // ---------------- barrier gradient rb and Sigma (reciprocal slacks are kept for the step-size phase)
     for (int q = MYR_TID; q < Q; q += MYR_NT) {
-#pragma unroll
+      const uint32_t fm = fix_sh[q];
+#pragma unroll 1
       for (int i = 0; i < NW; ++i) {
         const int id = S::zidx(P, q, i);
-        const Bnd bd = make_bnd(lb[id], ub[id], O.bound_relax);
-        double sg = 0.0, rbv = w[L.rb + q * NW + i];
-        if (bd.hasL) { const double sl = z[id] - bd.lbr; sg += zL[id] / sl; rbv -= mu / sl; }
-        if (bd.hasU) { const double su = bd.ubr - z[id]; sg += zU[id] / su; rbv += mu / su; }
+        const bool fixed = (fm >> i) & 1u;
+        double sg = 0.0, rbv = NQ(rb, q, i), r1 = 0.0, r2 = 0.0;
+        if (!fixed) {
+          const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = z[id];
+          if (lo > -INFINITY) { r1 = 1.0 / (x - lo); sg += zL[id] * r1; rbv -= mu * r1; }
+          if (hi < INFINITY) { r2 = 1.0 / (hi - x); sg += zU[id] * r2; rbv += mu * r2; }
+        }
+        NQ(rsl, q, i) = r1; NQ(rsu, q, i) = r2;
         sig_sh[q * NW + i] = sg;
-        w[L.rb + q * NW + i] = bd.fixed ? 0.0 : rbv;
+        NQ(rb, q, i) = fixed ? 0.0 : rbv;
       }
     }
-    (void)dphi_lin;
     MYR_SYNC();
 
+    MYR_PH(2);
     // ---------------- K2: KKT solve with inertia correction (IPOPT Algorithm IC)
     double delta = 0.0;
     bool ok = false;
     for (int tries = 0; tries < 60; ++tries) {
+#ifdef MYR_COUNT_KKT
+      ++n_kkt;
+#endif
       // accurate steps only matter near the solution: refine the linear solve in the end game only
       ok = kkt_solve<S>(P, L, w, sig_sh, fix_sh, delta, O.delta_c, cr, red, O.delta_reg, E0 < 1e-3 ? O.max_refine : 0);
       if (ok) break;
@@ -891,65 +956,66 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     if (!ok) { status = ST_INERTIA; break; }
     if (delta > 0.0) delta_last = delta;
 
+    MYR_PH(3);
     // ---------------- step sizes (fraction to the boundary), bound-multiplier steps, merit derivative
-    double a_pr = 1.0, a_du = 1.0, dphi = 0.0, dHd = 0.0;
+    // alpha = min(1, tau / max_i(-d_i / slack_i)): one division at the end instead of one per variable
+    double m_pr = 0.0, m_du = 0.0, dphi = 0.0, dHd = 0.0;
     for (int q = MYR_TID; q < Q; q += MYR_NT) {
       const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-      const double* Gq = w + L.G + q * NC * NW;
-      const double* Fq = w + L.F + q * NC * NW;
-      // J^T (lam + dlam) part of  H dz = -(rb + J^T dlam): dz^T H dz = -dz.(rb + J^T dlam)
-      double jt[NW], jl[NW];
+      double lp[NC], ls[NC], dp[NC], ds[NC];
 #pragma unroll
-      for (int i = 0; i < NW; ++i) { jt[i] = 0.0; jl[i] = 0.0; }
-      if (jp >= 0) {
-#pragma unroll
-        for (int rr = 0; rr < NC; ++rr) {
-          const double d = w[L.dlam + jp * NC + rr], l = lam[S::cidx(P, jp, rr)];
-#pragma unroll
-          for (int i = 0; i < NW; ++i) { jt[i] += Gq[rr * NW + i] * d; jl[i] += Gq[rr * NW + i] * l; }
-        }
+      for (int rr = 0; rr < NC; ++rr) {
+        lp[rr] = jp >= 0 ? lam[S::cidx(P, jp, rr)] : 0.0;
+        ls[rr] = js >= 0 ? lam[S::cidx(P, js, rr)] : 0.0;
+        dp[rr] = jp >= 0 ? NS(dlam, jp, rr) : 0.0;
+        ds[rr] = js >= 0 ? NS(dlam, js, rr) : 0.0;
       }
-      if (js >= 0) {
-#pragma unroll
-        for (int rr = 0; rr < NC; ++rr) {
-          const double d = w[L.dlam + js * NC + rr], l = lam[S::cidx(P, js, rr)];
-#pragma unroll
-          for (int i = 0; i < NW; ++i) { jt[i] += Fq[rr * NW + i] * d; jl[i] += Fq[rr * NW + i] * l; }
-        }
-      }
-#pragma unroll
+      const uint32_t fm = fix_sh[q];
+#pragma unroll 1
       for (int i = 0; i < NW; ++i) {
         const int id = S::zidx(P, q, i);
-        const Bnd bd = make_bnd(lb[id], ub[id], O.bound_relax);
-        const double d = w[L.dz + q * NW + i];
+        const bool fixed = (fm >> i) & 1u;
+        // J^T (lam + dlam) part of  H dz = -(rb + J^T dlam): dz^T H dz = -dz.(rb + J^T dlam)
+        double jt = 0.0, jl = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < NC; ++rr) {
+          const double g = NQ(G, q, rr * NW + i), f_ = NQ(F, q, rr * NW + i);
+          jt += g * dp[rr] + f_ * ds[rr];
+          jl += g * lp[rr] + f_ * ls[rr];
+        }
+        const double d = NQ(dz, q, i);
         double dl = 0.0, du = 0.0;
-        if (!bd.fixed) {
-          const double rbv = w[L.rb + q * NW + i];
-          dHd -= d * (rbv + jt[i]);
-          dphi += d * (rbv - jl[i]);  // barrier-objective gradient = rb - J^T lam
-          if (bd.hasL) {
-            const double sl = z[id] - bd.lbr;
-            dl = mu / sl - zL[id] - zL[id] / sl * d;
-            if (d < 0.0) a_pr = fmin(a_pr, -tau * sl / d);
-            if (dl < 0.0) a_du = fmin(a_du, -tau * zL[id] / dl);
+        if (!fixed) {
+          const double rbv = NQ(rb, q, i);
+          dHd -= d * (rbv + jt);
+          dphi += d * (rbv - jl);  // barrier-objective gradient = rb - J^T lam
+          const double r1 = NQ(rsl, q, i), r2 = NQ(rsu, q, i);
+          if (r1 != 0.0) {
+            const double zl = zL[id];
+            dl = mu * r1 - zl - zl * r1 * d;
+            m_pr = fmax(m_pr, -d * r1);
+            if (dl < 0.0) m_du = fmax(m_du, -dl / zl);
           }
-          if (bd.hasU) {
-            const double su = bd.ubr - z[id];
-            du = mu / su - zU[id] + zU[id] / su * d;
-            if (d > 0.0) a_pr = fmin(a_pr, tau * su / d);
-            if (du < 0.0) a_du = fmin(a_du, -tau * zU[id] / du);
+          if (r2 != 0.0) {
+            const double zu = zU[id];
+            du = mu * r2 - zu + zu * r2 * d;
+            m_pr = fmax(m_pr, d * r2);
+            if (du < 0.0) m_du = fmax(m_du, -du / zu);
           }
         }
-        w[L.dzL + q * NW + i] = dl;
-        w[L.dzU + q * NW + i] = du;
+        NQ(dzL, q, i) = dl;
+        NQ(dzU, q, i) = du;
       }
     }
-    a_pr = block_min(a_pr, red);
-    a_du = block_min(a_du, red);
+    m_pr = block_max(m_pr, red);
+    m_du = block_max(m_du, red);
     dphi = block_sum(dphi, red);
     dHd = block_sum(dHd, red);
     if (!(dphi == dphi)) { status = ST_NAN; break; }
+    const double a_pr = m_pr > tau ? tau / m_pr : 1.0;
+    const double a_du = m_du > tau ? tau / m_du : 1.0;
 
+    MYR_PH(4);
     // ---------------- l1-merit backtracking line search
     if (c1 > 0.0) {
       const double nu_trial = (dphi + 0.5 * fmax(dHd, 0.0)) / ((1.0 - O.rho) * c1);
@@ -964,15 +1030,20 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     for (int ls = 0; ls < O.max_ls; ++ls) {
       double blog = 0.0;
       for (int q = MYR_TID; q < Q; q += MYR_NT) {
-#pragma unroll
+        const uint32_t fm = fix_sh[q];
+        LogProd lpq;
+#pragma unroll 1
         for (int i = 0; i < NW; ++i) {
           const int id = S::zidx(P, q, i);
-          const Bnd bd = make_bnd(lb[id], ub[id], O.bound_relax);
-          const double x = z[id] + alpha * w[L.dz + q * NW + i];
+          const double x = z[id] + alpha * NQ(dz, q, i);
           zt[id] = x;
-          if (bd.hasL) blog += log(x - bd.lbr);
-          if (bd.hasU) blog += log(bd.ubr - x);
+          if (!((fm >> i) & 1u)) {
+            const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i);
+            if (lo > -INFINITY) lpq.mul(x - lo);
+            if (hi < INFINITY) lpq.mul(hi - x);
+          }
         }
+        blog += lpq.value();
       }
       MYR_SYNC();
       f_t = eval_nodes<S, 0>(P, L, zt, lam, w, red, mlp_scr);
@@ -986,37 +1057,42 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     }
     if (!accepted) { status = (E0 <= O.acceptable_tol) ? ST_ACCEPTABLE : ST_LINESEARCH; break; }
 
+    MYR_PH(5);
     // ---------------- accept: primal, equality multipliers, bound multipliers (with the kappa_sigma safeguard)
     for (int q = MYR_TID; q < Q; q += MYR_NT) {
-#pragma unroll
+      const uint32_t fm = fix_sh[q];
+#pragma unroll 1
       for (int i = 0; i < NW; ++i) {
+        if ((fm >> i) & 1u) continue;
         const int id = S::zidx(P, q, i);
-        const Bnd bd = make_bnd(lb[id], ub[id], O.bound_relax);
-        if (bd.fixed) continue;
         const double x = zt[id];
         z[id] = x;
-        if (bd.hasL) {
-          const double sl = x - bd.lbr;
-          double v = zL[id] + a_du * w[L.dzL + q * NW + i];
-          v = fmax(fmin(v, O.kappa_sigma * mu / sl), mu / (O.kappa_sigma * sl));
+        const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i);
+        if (lo > -INFINITY) {
+          const double ms = mu / (x - lo);
+          double v = zL[id] + a_du * NQ(dzL, q, i);
+          v = fmax(fmin(v, O.kappa_sigma * ms), ms / O.kappa_sigma);
           zL[id] = v;
         }
-        if (bd.hasU) {
-          const double su = bd.ubr - x;
-          double v = zU[id] + a_du * w[L.dzU + q * NW + i];
-          v = fmax(fmin(v, O.kappa_sigma * mu / su), mu / (O.kappa_sigma * su));
+        if (hi < INFINITY) {
+          const double ms = mu / (hi - x);
+          double v = zU[id] + a_du * NQ(dzU, q, i);
+          v = fmax(fmin(v, O.kappa_sigma * ms), ms / O.kappa_sigma);
           zU[id] = v;
         }
       }
     }
     for (int j = MYR_TID; j < St; j += MYR_NT)
 #pragma unroll
-      for (int r = 0; r < NC; ++r) lam[S::cidx(P, j, r)] += alpha * w[L.dlam + j * NC + r];
+      for (int r = 0; r < NC; ++r) lam[S::cidx(P, j, r)] += alpha * NS(dlam, j, r);
     MYR_SYNC();
     ++it;
   }
   InstResult res;
   res.f = f; res.E0 = E0; res.cinf = cinf; res.status = status; res.iters = it;
+#ifdef MYR_COUNT_KKT
+  res.iters = it + 10000 * n_kkt;  // experiment: number of KKT factorisations in the upper digits
+#endif
   return res;
 }
 

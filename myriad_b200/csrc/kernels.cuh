@@ -434,10 +434,10 @@ __host__ __device__ inline void kkt_instance(const Problem& P, int b, const doub
   for (int q = MYR_TID; q < L.Q; q += MYR_NT) {
     const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
     for (int i = 0; i < S::NC * S::NW; ++i) {
-      w[L.G + q * S::NC * S::NW + i] = jp >= 0 ? Jb[((long long)jp * S::kMaxStageNodes + S::phi_slot(P, q)) * S::NC * S::NW + i] : 0.0;
-      w[L.F + q * S::NC * S::NW + i] = js >= 0 ? Jb[((long long)js * S::kMaxStageNodes + S::psi_slot(P, q)) * S::NC * S::NW + i] : 0.0;
+      NQ(G, q, i) = jp >= 0 ? Jb[((long long)jp * S::kMaxStageNodes + S::phi_slot(P, q)) * S::NC * S::NW + i] : 0.0;
+      NQ(F, q, i) = js >= 0 ? Jb[((long long)js * S::kMaxStageNodes + S::psi_slot(P, q)) * S::NC * S::NW + i] : 0.0;
     }
-    for (int i = 0; i < S::NWP; ++i) w[L.W + q * S::NWP + i] = Hblk[((long long)b * L.Q + q) * S::NWP + i];
+    for (int i = 0; i < S::NWP; ++i) NQ(W, q, i) = Hblk[((long long)b * L.Q + q) * S::NWP + i];
     uint32_t fm = 0;
     for (int i = 0; i < S::NW; ++i) {
       const int id = S::zidx(P, q, i);
@@ -445,18 +445,18 @@ __host__ __device__ inline void kkt_instance(const Problem& P, int b, const doub
       const bool fx = isinf(sg);
       if (fx) fm |= 1u << i;
       sig_sh[q * S::NW + i] = fx ? 0.0 : sg;
-      w[L.rb + q * S::NW + i] = fx ? 0.0 : rhs_z[(long long)b * P.nvars + id];
+      NQ(rb, q, i) = fx ? 0.0 : rhs_z[(long long)b * P.nvars + id];
     }
     fix_sh[q] = fm;
   }
   for (int j = MYR_TID; j < L.St; j += MYR_NT)
-    for (int r = 0; r < S::NC; ++r) w[L.c + j * S::NC + r] = rhs_c[(long long)b * P.ncon + S::cidx(P, j, r)];
+    for (int r = 0; r < S::NC; ++r) NS(c, j, r) = rhs_c[(long long)b * P.ncon + S::cidx(P, j, r)];
   MYR_SYNC();
   const bool ok = kkt_solve<S>(P, L, w, sig_sh, fix_sh, dw, dc, cr, red);
   for (int q = MYR_TID; q < L.Q; q += MYR_NT)
-    for (int i = 0; i < S::NW; ++i) dz[(long long)b * P.nvars + S::zidx(P, q, i)] = w[L.dz + q * S::NW + i];
+    for (int i = 0; i < S::NW; ++i) dz[(long long)b * P.nvars + S::zidx(P, q, i)] = NQ(dz, q, i);
   for (int j = MYR_TID; j < L.St; j += MYR_NT)
-    for (int r = 0; r < S::NC; ++r) dlam[(long long)b * P.ncon + S::cidx(P, j, r)] = w[L.dlam + j * S::NC + r];
+    for (int r = 0; r < S::NC; ++r) dlam[(long long)b * P.ncon + S::cidx(P, j, r)] = NS(dlam, j, r);
   if (MYR_TID == 0 && inertia_ok) inertia_ok[b] = ok ? 1 : 0;
 }
 
@@ -552,8 +552,24 @@ inline IpmOpts make_opts(const MyrIpmOpts* o) {
   return r;
 }
 
+// Launch shape of the per-instance interior-point kernel: one CTA per instance; 128 threads stride over nodes / stages
+// (256 for the cooperative tensor-core MLP pass of NODE systems).  kMinBlocks bounds registers so that several
+// instances are resident per SM: the kernel is latency-bound, resident warps are what hides it.
+#ifndef MYR_IPM_MINBLOCKS
+#define MYR_IPM_MINBLOCKS 2
+#endif
 template <class S>
-__global__ void __launch_bounds__(256) ipm_kernel(Problem P, IpmOpts O, IpmIO io, int cr_in_smem) {
+struct IpmLaunch {
+  // Hermite-Simpson has 2N+1 nodes and 2n-row stages: its CR scratch does not fit shared memory next to a second
+  // CTA anyway, so it runs 256 threads with the full register file
+  static constexpr bool kWide = Layout<S>::kCoopMlp || S::kMaxStageNodes >= 3;
+  static constexpr int kThreads = kWide ? 256 : 128;
+  static constexpr int kMinBlocks = kWide ? 1 : MYR_IPM_MINBLOCKS;
+  static int threads(int Q) { const int t = threads_for(Q, Layout<S>::kCoopMlp); return t < kThreads ? t : kThreads; }
+};
+
+template <class S>
+__global__ void __launch_bounds__(IpmLaunch<S>::kThreads, IpmLaunch<S>::kMinBlocks) ipm_kernel(Problem P, IpmOpts O, IpmIO io, int cr_in_smem) {
   extern __shared__ double smem[];
   const Layout<S> L(P);
   double* red = smem;
@@ -582,10 +598,20 @@ int sys_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const doub
     const IpmOpts O = make_opts(opts);
     const SmemPlan<S> sp(P);
     if (sp.total > 48 * 1024) cudaFuncSetAttribute(ipm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
-    ipm_kernel<S><<<B, threads_for(L.Q, Layout<S>::kCoopMlp), sp.total, (cudaStream_t)stream>>>(P, O, io, sp.cr_in_smem ? 1 : 0);
+    ipm_kernel<S><<<B, IpmLaunch<S>::threads(L.Q), sp.total, (cudaStream_t)stream>>>(P, O, io, sp.cr_in_smem ? 1 : 0);
     return cuda_check("myr_ipm_solve");
   });
 }
+
+#ifdef MYR_PROFILE_PHASES
+extern "C" int myr_debug_phase_cycles(double* out16, int reset) {
+  unsigned long long h[16];
+  cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof(h));
+  for (int i = 0; i < 16; ++i) out16[i] = (double)h[i];
+  if (reset) { memset(h, 0, sizeof(h)); cudaMemcpyToSymbol(g_phase_cycles, h, sizeof(h)); }
+  return 0;
+}
+#endif
 
 template <class Sys>
 int sys_host_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const double* z0, const double* lb, const double* ub,

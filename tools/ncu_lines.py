@@ -30,7 +30,10 @@ for cb in cubins:
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kre], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = None
-agg = collections.Counter(); inst = collections.Counter()
+agg = collections.Counter(); inst = collections.Counter(); reasons = collections.defaultdict(collections.Counter)
+RS = ["stall_barrier", "stall_long_sb", "stall_short_sb", "stall_wait", "stall_lg", "stall_mio", "stall_math", "stall_no_inst",
+      "stall_branch_resolving", "stall_dispatch", "stall_not_selected", "stall_selected", "stall_sleep", "stall_misc"]
+totals = collections.Counter()
 base = None
 tot = 0
 for r in rows:
@@ -45,7 +48,11 @@ for r in rows:
     key = linemap.get(a - base, ("?", 0))
     agg[key] += s; tot += s
     inst[key] += int(d.get("Instructions Executed") or 0)
+    for rname in RS:
+      v = int(d.get(rname) or 0)
+      reasons[key][rname] += v; totals[rname] += v
 print(f"total samples {tot}")
+print("by reason: " + ", ".join(f"{k[6:]} {100*v/max(tot,1):.1f}%" for k, v in totals.most_common(8)))
 srcs = {}
 for (f, l), s in agg.most_common(top):
   if f not in srcs:
@@ -56,4 +63,5 @@ for (f, l), s in agg.most_common(top):
     else:
       srcs[f] = []
   text = srcs[f][l - 1].strip()[:100] if 0 < l <= len(srcs[f]) else ""
-  print(f"{100*s/max(tot,1):5.1f}% {inst[(f,l)]:>10d} inst  {f}:{l}  {text}")
+  rs = ", ".join(f"{k[6:]} {100*v/max(s,1):.0f}%" for k, v in reasons[(f, l)].most_common(3))
+  print(f"{100*s/max(tot,1):5.1f}% {inst[(f,l)]:>10d} inst  {f}:{l}  [{rs}]  {text}")
