@@ -32,6 +32,12 @@ SYSTEM, INTERVALS = "CARTPOLE", 100
 METRIC = "trajopt solves/sec (CARTPOLE collocation N=100, batched)"
 
 
+def workload_name(quadrature: str) -> str:
+  """config.workload, identical in both arms (the reference arm times a bounded sample of the same workload)"""
+  return (f"{SYSTEM} COLLOCATION {quadrature} intervals={INTERVALS}, batch=1024 random x0 (seed 2019, spread 0.1), fp64 "
+          "(BASELINE.json configs[1])")
+
+
 def parse():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
@@ -72,8 +78,8 @@ def reference_arm(args):
   line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": len(vals),
           "warmup": args.warmup, "ms_per_step": 1e3 * secs / len(vals), "higher_is_better": True, "scaling": "weak",
           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-          "config": {"workload": f"{SYSTEM} COLLOCATION {args.quadrature} intervals={INTERVALS}, random x0 (seed 2019, spread 0.1)",
-                     "batch_per_step": cores},
+          "config": {"workload": workload_name(args.quadrature), "batch_per_step": cores,
+                     "sample": f"{cores} of the workload's instances per step (one SLSQP solve per host core)"},
           "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
                            "sample": f"{cores} instances per step, one SciPy-SLSQP solve per core (oracle restatement of the "
                                      "reference transcription; IPOPT/jax are not installable here)"},
@@ -336,9 +342,7 @@ def b200_arm(args):
       "metric": METRIC, "value": total * args.steps / (ms_dev * 1e-3), "unit": "solves/s", "n_gpus": world, "steps": args.steps,
       "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "f64", "data": "synthetic",
-      "config": {"workload": f"{SYSTEM} COLLOCATION {args.quadrature} intervals={INTERVALS}, batch={B}/GPU random x0 "
-                             f"(seed {hp.seed}, spread {hp.start_spread}), fp64, max_iter={hp.max_iter}, tol=1e-8",
-                 "batch_per_gpu": B, "nvars": sz.nvars, "ncon": sz.ncon,
+      "config": {"workload": workload_name(args.quadrature), "batch_per_gpu": B, "max_iter": hp.max_iter, "tol": 1e-8, "nvars": sz.nvars, "ncon": sz.ncon,
                  "l2": "256 MB buffer written between timed steps (outside the timed events)",
                  "step": "myr_ipm_solve + myr_rollout_cost + pack" + (" + NCCL all_gather" if world > 1 else "")},
       "solved": n_ok_all, "instances": total, "success_rate": n_ok_all / total,

@@ -66,6 +66,39 @@ class SimpleCaseWithBounds(FiniteHorizonControlSystem):
                      terminal_cost=False, discrete=False, device_name="SIMPLECASEWITHBOUNDS", params=[A, C])
 
 
+class Bioreactor(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/bioreactor.py:36-83"""
+
+  def __init__(self, K=2., G=1., D=1., M=1., x_0=(.5, .1), T=2.):
+    super().__init__(x_0=np.array([x_0[0]], dtype=np.float64), x_T=None, T=T, bounds=np.array([[0., 1.], [0., M]]),
+                     terminal_cost=False, discrete=False, device_name="BIOREACTOR", params=[K, G, D])
+
+
+class Glucose(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/glucose.py:43-104"""
+
+  def __init__(self, a=1., b=1., c=1., A=2., l=.5, x_0=(.75, 0.), T=.2):
+    super().__init__(x_0=np.array([x_0[0], x_0[1]], dtype=np.float64), x_T=None, T=T,
+                     bounds=np.array([[0., 1.], [0., 1.], [0., 0.01]]), terminal_cost=False, discrete=False,
+                     device_name="GLUCOSE", params=[a, b, c, A, l])
+
+
+class Harvest(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/harvest.py:32-62 (time-dependent running cost)"""
+
+  def __init__(self, A=5., k=10., m=.2, M=1., x_0=.4, T=10.):
+    super().__init__(x_0=np.array([x_0], dtype=np.float64), x_T=None, T=T, bounds=np.array([[-np.inf, np.inf], [0., M]]),
+                     terminal_cost=False, discrete=False, device_name="HARVEST", params=[A, k, m])
+
+
+class TimberHarvest(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/timber_harvest.py:41-85 (time-dependent running cost)"""
+
+  def __init__(self, r=0., k=1., x_0=100., T=5.):
+    super().__init__(x_0=np.array([x_0], dtype=np.float64), x_T=None, T=T, bounds=np.array([[0., 20_000.], [0., 1.]]),
+                     terminal_cost=False, discrete=False, device_name="TIMBERHARVEST", params=[r, k])
+
+
 class NodeSystem(FiniteHorizonControlSystem):
   """myriad/systems/neural_ode/node_system.py:14-42: a system whose (parametrized) dynamics is the neural-ODE MLP of
   myriad/neural_ode/create_node.py:110-117 applied to concat(x, u), while cost, bounds, horizon, start/end states and
@@ -145,12 +178,12 @@ class SystemType(Enum):
   SIMPLECASEWITHBOUNDS = SimpleCaseWithBounds
   CANCERTREATMENT = CancerTreatment
   EPIDEMICSEIRN = _NotOnDevice("EPIDEMICSEIRN")
-  HARVEST = _NotOnDevice("HARVEST")
+  HARVEST = Harvest
   HIVTREATMENT = _NotOnDevice("HIVTREATMENT")
   BEARPOPULATIONS = _NotOnDevice("BEARPOPULATIONS")
-  GLUCOSE = _NotOnDevice("GLUCOSE")
-  TIMBERHARVEST = _NotOnDevice("TIMBERHARVEST")
-  BIOREACTOR = _NotOnDevice("BIOREACTOR")
+  GLUCOSE = Glucose
+  TIMBERHARVEST = TimberHarvest
+  BIOREACTOR = Bioreactor
   PREDATORPREY = _NotOnDevice("PREDATORPREY")
   INVASIVEPLANT = _NotOnDevice("INVASIVEPLANT")
   ROCKETLANDING = _NotOnDevice("ROCKETLANDING")

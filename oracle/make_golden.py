@@ -50,6 +50,15 @@ CASES = {
   "s_cancer_hs_10": ("CANCERTREATMENT", "COLLOCATION", "HERMITE_SIMPSON", "RK4", 10, 1),
   "s_cancer_shooting_2x10_midpoint": ("CANCERTREATMENT", "SHOOTING", "TRAPEZOIDAL", "MIDPOINT", 2, 10),
   "s_cancer_shooting_2x10_euler": ("CANCERTREATMENT", "SHOOTING", "TRAPEZOIDAL", "EULER", 2, 10),
+  # further SystemType members with generated device code (incl. the two time-dependent running costs)
+  "x_mould_trap_10": ("MOULDFUNGICIDE", "COLLOCATION", "TRAPEZOIDAL", "HEUN", 10, 1),
+  "x_bioreactor_hs_8": ("BIOREACTOR", "COLLOCATION", "HERMITE_SIMPSON", "RK4", 8, 1),
+  "x_scwb_shooting_4x5_heun": ("SIMPLECASEWITHBOUNDS", "SHOOTING", "TRAPEZOIDAL", "HEUN", 4, 5),
+  "x_glucose_trap_10": ("GLUCOSE", "COLLOCATION", "TRAPEZOIDAL", "HEUN", 10, 1),
+  "x_harvest_trap_10": ("HARVEST", "COLLOCATION", "TRAPEZOIDAL", "HEUN", 10, 1),
+  "x_harvest_shooting_2x8_rk4": ("HARVEST", "SHOOTING", "TRAPEZOIDAL", "RK4", 2, 8),
+  "x_timber_hs_6": ("TIMBERHARVEST", "COLLOCATION", "HERMITE_SIMPSON", "RK4", 6, 1),
+  "x_timber_shooting_3x6_midpoint": ("TIMBERHARVEST", "SHOOTING", "TRAPEZOIDAL", "MIDPOINT", 3, 6),
   # BASELINE config C5: CARTPOLE with neural-ODE MLP dynamics (3 x 64), planned the way the reference's
   # plan_with_node_model does (myriad/utils.py:230-242: system.dynamics <- net.apply(params, append(x, u))).
   # Weights: tests/golden/node_cartpole_64x64x64.npz (tools/fit_node.py).
@@ -89,6 +98,7 @@ SOLVE_CASES = [
   "c1_simplecase_shooting_10x100_heun", "t_simplecase_shooting_1x50_heun", "t_simplecase_trap_50",
   "t_simplecase_hs_50", "s_vanderpol_trap_20", "s_cancer_trap_20", "s_cartpole_trap_10",
   "t_simplecase_shooting_20x3_heun", "s_vanderpol_hs_10", "n_node_cartpole_trap_10",
+  "x_mould_trap_10", "x_glucose_trap_10", "x_harvest_trap_10", "x_scwb_shooting_4x5_heun",
 ]
 
 

@@ -140,6 +140,92 @@ class CancerTreatment(OracleSystem):
     return self.params["a"] * x[..., 0] ** 2 + u[..., 0] ** 2  # cancer_treatment.py:76
 
 
+class MouldFungicide(OracleSystem):
+  """myriad/systems/lenhart/mould_fungicide.py:29-66"""
+
+  def __init__(self, r=0.3, M=10., A=10., x_0=1.0, T=5):
+    super().__init__("MOULDFUNGICIDE", np.array([x_0]), None, T, np.array([[0., 5.], [0., 5.]]), False, dict(r=r, M=M, A=A))
+
+  def dynamics(self, x, u):
+    p = self.params
+    return _stack([p["r"] * (p["M"] - x[..., 0]) - u[..., 0] * x[..., 0]], x)  # mould_fungicide.py:52
+
+  def cost(self, x, u, t):
+    return self.params["A"] * x[..., 0] ** 2 + u[..., 0] ** 2  # mould_fungicide.py:66
+
+
+class Bioreactor(OracleSystem):
+  """myriad/systems/lenhart/bioreactor.py:36-83"""
+
+  def __init__(self, K=2., G=1., D=1., M=1., x_0=(.5, .1), T=2.):
+    super().__init__("BIOREACTOR", np.array([x_0[0]]), None, T, np.array([[0., 1.], [0., M]]), False, dict(K=K, G=G, D=D))
+
+  def dynamics(self, x, u):
+    p = self.params
+    return _stack([p["G"] * u[..., 0] * x[..., 0] - p["D"] * x[..., 0] ** 2], x)  # bioreactor.py:67
+
+  def cost(self, x, u, t):
+    return -self.params["K"] * x[..., 0] + u[..., 0]  # bioreactor.py:83
+
+
+class SimpleCaseWithBounds(OracleSystem):
+  """myriad/systems/lenhart/simple_case_with_bounds.py:25-56"""
+
+  def __init__(self, A=1., C=4., M_1=-1., M_2=2., x_0=1., T=1.):
+    super().__init__("SIMPLECASEWITHBOUNDS", np.array([x_0]), None, T, np.array([[0., 3.], [M_1, M_2]]), False, dict(A=A, C=C))
+
+  def dynamics(self, x, u):
+    return _stack([-0.5 * x[..., 0] ** 2 + self.params["C"] * u[..., 0]], x)  # simple_case_with_bounds.py:51
+
+  def cost(self, x, u, t):
+    return -self.params["A"] * x[..., 0] + u[..., 0] ** 2  # simple_case_with_bounds.py:56
+
+
+class Glucose(OracleSystem):
+  """myriad/systems/lenhart/glucose.py:43-104"""
+
+  def __init__(self, a=1., b=1., c=1., A=2., l=.5, x_0=(.75, 0.), T=.2):
+    super().__init__("GLUCOSE", np.array([x_0[0], x_0[1]]), None, T, np.array([[0., 1.], [0., 1.], [0., 0.01]]), False,
+                     dict(a=a, b=b, c=c, A=A, l=l))
+
+  def dynamics(self, x, u):
+    p = self.params
+    return _stack([-p["a"] * x[..., 0] - p["b"] * x[..., 1], -p["c"] * x[..., 1] + u[..., 0]], x)  # glucose.py:78-81
+
+  def cost(self, x, u, t):
+    p = self.params
+    return 100_000 * (p["A"] * (x[..., 0] - p["l"]) ** 2 + u[..., 0] ** 2)  # glucose.py:104
+
+
+class Harvest(OracleSystem):
+  """myriad/systems/lenhart/harvest.py:32-62 (time-dependent cost)"""
+
+  def __init__(self, A=5., k=10., m=.2, M=1., x_0=.4, T=10.):
+    super().__init__("HARVEST", np.array([x_0]), None, T, np.array([[-np.inf, np.inf], [0., M]]), False, dict(A=A, k=k, m=m))
+
+  def dynamics(self, x, u):
+    return _stack([-(self.params["m"] + u[..., 0]) * x[..., 0]], x)  # harvest.py:57
+
+  def cost(self, x, u, t):
+    p = self.params
+    return -p["A"] * (p["k"] * t / (t + 1)) * x[..., 0] * u[..., 0] + u[..., 0] ** 2  # harvest.py:62
+
+
+class TimberHarvest(OracleSystem):
+  """myriad/systems/lenhart/timber_harvest.py:41-85 (time-dependent cost)"""
+
+  def __init__(self, r=0., k=1., x_0=100., T=5.):
+    super().__init__("TIMBERHARVEST", np.array([x_0]), None, T, np.array([[0., 20_000.], [0., 1.]]), False, dict(r=r, k=k))
+
+  def dynamics(self, x, u):
+    return _stack([self.params["k"] * x[..., 0] * u[..., 0]], x)  # timber_harvest.py:64
+
+  def cost(self, x, u, t):
+    xp = _xp(x)
+    e = xp.exp(-self.params["r"] * (t if xp is np else torch.as_tensor(t, dtype=x.dtype)))
+    return -e * x[..., 0] * (1 - u[..., 0])  # timber_harvest.py:85
+
+
 class NodeSystem(OracleSystem):
   """NODE-dynamics wrapper: myriad/systems/neural_ode/node_system.py:14-42 with the MLP of
   myriad/neural_ode/create_node.py:110-117 (hk.Linear = x @ w + b, sigmoid between layers).
@@ -190,6 +276,12 @@ SYSTEMS = {
   "CARTPOLE": CartPole,
   "VANDERPOL": VanDerPol,
   "CANCERTREATMENT": CancerTreatment,
+  "MOULDFUNGICIDE": MouldFungicide,
+  "BIOREACTOR": Bioreactor,
+  "SIMPLECASEWITHBOUNDS": SimpleCaseWithBounds,
+  "GLUCOSE": Glucose,
+  "HARVEST": Harvest,
+  "TIMBERHARVEST": TimberHarvest,
 }
 
 

@@ -151,7 +151,9 @@ def test_host_twin_ipm_matches_reference_solve(ML, case):
   ref = float(fx["sol_cost"])
   # SciPy's default ftol=1e-6 leaves SLSQP up to ~3e-5 short of the optimum on the flat SIMPLECASE objectives
   assert abs(out["obj"][0] - ref) <= 5e-5 * max(1.0, abs(ref))
-  assert out["obj"][0] <= ref + 1e-7 * max(1.0, abs(ref))
+  # the IPM is never worse than SLSQP beyond what SLSQP's own infeasibility buys it (first-order: |lam|_1 * |c_ref|_inf)
+  slack = float(np.abs(out["lam"][0]).sum() * fx["sol_con_inf"])
+  assert out["obj"][0] <= ref + 1e-7 * max(1.0, abs(ref)) + slack
   # KKT conditions re-checked independently with the oracle's derivatives
   from oracle import nlp
   from oracle.systems import make_system

@@ -133,7 +133,10 @@ def test_k3_solution_matches_reference_solve(case):
   ref = float(fx["sol_cost"])
   # SciPy's default ftol=1e-6 leaves SLSQP up to ~3e-5 short of the optimum on the flat SIMPLECASE objectives
   assert abs(obj - ref) <= 5e-5 * max(1.0, abs(ref)), (obj, ref)
-  assert obj <= ref + 1e-7 * max(1.0, abs(ref))  # the IPM is converged tighter than SLSQP's ftol=1e-6
+  # the IPM is converged tighter than SLSQP's ftol=1e-6: never worse than SLSQP beyond what SLSQP's own infeasibility
+  # buys it (first-order: |lam|_1 * |c_ref|_inf)
+  slack = float(out["lam"][0].abs().sum()) * float(fx["sol_con_inf"])
+  assert obj <= ref + 1e-7 * max(1.0, abs(ref)) + slack
 
 
 @pytest.mark.parametrize("case", ["c2_cartpole_trap_100", "c2_cartpole_hs_100", "s_vanderpol_trap_20", "n_node_cartpole_trap_10"])
