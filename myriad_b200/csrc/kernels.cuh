@@ -269,8 +269,9 @@ template <class S>
 __global__ void __launch_bounds__(256) eval_kernel(Problem P, const double* __restrict__ z_all, const double* __restrict__ lam_all,
                                                    double* __restrict__ f_out, double* __restrict__ grad_out, double* __restrict__ c_out,
                                                    double* __restrict__ J_out, double* __restrict__ H_out) {
-  extern __shared__ double smem[];
-  constexpr int NW = S::NW, NC = S::NC, BLK = NC * NW, ROW = S::kMaxStageNodes * BLK, ROWP = ROW + 1;
+  extern __shared__ __align__(16) double smem[];
+  constexpr int NW = S::NW, NC = S::NC, BLK = NC * NW, ROW = S::kMaxStageNodes * BLK, ROWP = ROW + 2;
+  static_assert(ROW % 2 == 0, "stage rows must be a multiple of 16 bytes for the bulk stores");
   const Layout<S> L(P);
   const int Q = L.Q, St = L.St;
   double* red = smem;
@@ -347,16 +348,22 @@ __global__ void __launch_bounds__(256) eval_kernel(Problem P, const double* __re
       }
     }
     if (J_out) {
+      // one TMA bulk store (cp.async.bulk shared -> global, UBLKCP) per stage row: the 32 KB Jacobian of the instance
+      // leaves the SM without occupying load/store issue slots; the stores drain while c / H are written below
       double* Jb = J_out + (long long)b * jstride;
-      for (int o = threadIdx.x; o < (int)jstride; o += blockDim.x) {
-        const int j = o / ROW;
-        Jb[o] = sJ[o + j];  // row j starts at j * (ROW + 1)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      for (int j = threadIdx.x; j < St; j += blockDim.x) {
+        const unsigned src = (unsigned)__cvta_generic_to_shared(sJ + (size_t)j * ROWP);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(Jb + (size_t)j * ROW), "r"(src), "r"((unsigned)(ROW * sizeof(double))) : "memory");
       }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     if (want_h) {
       double* Hb = H_out + (long long)b * Q * S::NWP;
       for (int o = threadIdx.x; o < Q * S::NWP; o += blockDim.x) Hb[o] = sH[o];
     }
+    if (J_out) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory of the rows has been read
     __syncthreads();
   }
 }
@@ -385,7 +392,7 @@ int sys_eval(const MyrDesc* desc, int B, const double* z, const double* lam, dou
     if (B == 0) return (int)MYR_OK;
     if (!z) return fail(MYR_E_BADARG, "z is null%s", "");
     const Layout<S> L(P);
-    const size_t row = (size_t)S::kMaxStageNodes * S::NC * S::NW + 1;
+    const size_t row = (size_t)S::kMaxStageNodes * S::NC * S::NW + 2;
     size_t smd = 64 + 2 * (size_t)L.Q * S::NC + (Jblk ? (size_t)L.St * row : 0) + ((lam && Hblk) ? (size_t)L.Q * S::NWP : 0);
     if (Layout<S>::kCoopMlp) smd += (size_t)L.Q * (S::n + S::n * S::NW + S::NWP) + mlp_scratch_doubles<S>(P.mlp);
     const size_t sm = smd * sizeof(double);

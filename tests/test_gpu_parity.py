@@ -207,3 +207,95 @@ def test_rollout_matches_reference_fixture(case):
   torch.cuda.synchronize()
   np.testing.assert_allclose(xs[0].cpu().numpy(), fx["rollout_states"], rtol=1e-12, atol=1e-13)
   np.testing.assert_allclose(float(cost[0]), float(fx["rollout_cost"]), rtol=1e-12)
+
+
+# ----------------------------------------------------------------------------- full-size / edge-case properties
+def _batch(tr, B):
+  from myriad_b200 import problems as PR
+  x0 = PR.sample_x0(tr.system, B, device="cuda")
+  return (x0,) + tuple(PR.build_batch(tr, x0))
+
+
+@pytest.mark.parametrize("case,B", [("c3_vanderpol_shooting_1x50_heun", 8192), ("c4_cancer_shooting_1x100_heun", 16384),
+                                    ("c1_simplecase_shooting_10x100_heun", 256), ("c2_cartpole_hs_100", 128),
+                                    ("c5_node_cartpole_trap_100", 64)])
+def test_full_size_batches_satisfy_their_own_kkt_conditions(case, B):
+  """BASELINE.json batch sizes: size-independent properties instead of an oracle solve per instance -- every solved
+  instance is feasible to 1e-8, re-evaluating the returned point through K1 reproduces the reported objective and
+  constraint violation, and the stationarity residual grad f + J^T lam - zL + zU vanishes on the free variables."""
+  from myriad_b200 import problems as PR
+  tr = _tr(case)
+  eng = _eng(tr)
+  x0, z0, lb, ub = _batch(tr, B)
+  out = eng.ipm_solve(z0, lb, ub)
+  torch.cuda.synchronize()
+  ok = out["status"] == 0
+  assert float(ok.double().mean()) >= 0.97, torch.unique(out["status"], return_counts=True)
+  assert float(out["con_inf"][ok].max()) <= 1e-8
+  r = eng.eval(out["z"])
+  torch.cuda.synchronize()
+  np.testing.assert_allclose(r.f[ok].cpu().numpy(), out["obj"][ok].cpu().numpy(), rtol=1e-10, atol=1e-12)
+  assert float(r.c.abs().max(dim=1).values[ok].max()) <= 1e-8
+  # stationarity on a sample of instances (dense Jacobian is ncon x nvars per instance)
+  idx = torch.nonzero(ok)[:16, 0]
+  J = PR.dense_jacobian(tr, r.Jblk[idx])
+  rd = r.grad[idx] + torch.einsum("bcv,bc->bv", J, out["lam"][idx]) - out["zL"][idx] + out["zU"][idx]
+  free = (lb[idx] != ub[idx])
+  scale = 1.0 + out["lam"][idx].abs().max(dim=1, keepdim=True).values
+  assert float((rd.abs() * free / scale).max()) <= 1e-6
+  # bounds are respected (up to IPOPT's 1e-8 relative relaxation)
+  z = out["z"][ok]
+  assert bool((z >= lb[ok] - 1e-8 * (1 + lb[ok].abs())).all()) and bool((z <= ub[ok] + 1e-8 * (1 + ub[ok].abs())).all())
+
+
+def test_empty_batch_and_bad_arguments():
+  from myriad_b200 import _lib as ML
+  tr = _tr("s_cartpole_trap_10")
+  eng = _eng(tr)
+  s = eng.sizes
+  z = torch.empty(0, s.nvars, dtype=torch.float64, device="cuda")
+  r = eng.eval(z)  # B = 0 is a no-op, not an error
+  assert r.f.shape == (0,)
+  out = eng.ipm_solve(z, z.clone(), z.clone())
+  assert out["z"].shape == (0, s.nvars)
+  with pytest.raises(ML.MyriadError):  # CPU tensors are rejected: there is no CPU fallback
+    eng.eval(torch.zeros(1, s.nvars, dtype=torch.float64))
+  with pytest.raises(ML.MyriadError):  # fp32 is rejected: the path is fp64 like the reference (run.py:15)
+    eng.eval(torch.zeros(1, s.nvars, dtype=torch.float32, device="cuda"))
+
+
+@pytest.mark.parametrize("case", ["c2_cartpole_trap_100", "c2_cartpole_hs_100", "s_cartpole_shooting_5x4_heun", "n_node_cartpole_trap_10"])
+def test_k1_jacobian_is_the_derivative_of_k1_constraints(case):
+  """Linearity property, no oracle involved: J(z) v matches a central difference of c along v, grad f . v that of f."""
+  from myriad_b200 import problems as PR
+  fx = load(case)
+  tr = _tr(case)
+  eng = _eng(tr)
+  rng = np.random.default_rng(5)
+  z = fx["z"]
+  v = rng.standard_normal(z.shape)
+  eps = 1e-6
+  pts = _dev(np.stack([z, z + eps * v, z - eps * v]))
+  r = eng.eval(pts)
+  torch.cuda.synchronize()
+  J = PR.dense_jacobian(tr, r.Jblk[:1])[0].cpu().numpy()
+  c = r.c.cpu().numpy(); f = r.f.cpu().numpy()
+  np.testing.assert_allclose(J @ v, (c[1] - c[2]) / (2 * eps), rtol=1e-6, atol=1e-6)
+  np.testing.assert_allclose(r.grad[0].cpu().numpy() @ v, (f[1] - f[2]) / (2 * eps), rtol=1e-6, atol=1e-6)
+
+
+def test_plan_with_node_model_surface():
+  """myriad/utils.py:230-242 through the mirrored surface: NeuralODE + plan_with_node_model on the committed weights."""
+  from myriad_b200.config import Config, HParams, OptimizerType
+  from myriad_b200.neural_ode import NeuralODE, plan_with_node_model
+  from myriad_b200.systems import SystemType
+  from tests.cases import GOLDEN
+  import os
+  hp = HParams(system=SystemType.CARTPOLE, optimizer=OptimizerType.COLLOCATION, intervals=10, hidden_layers=(64, 64, 64))
+  node = NeuralODE(hp, Config(verbose=False, plot=False))
+  node.load_params(os.path.join(GOLDEN, "node_cartpole_64x64x64.npz"))
+  x, u = plan_with_node_model(node)
+  fx = load("n_node_cartpole_trap_10")
+  assert x.shape == fx["sol_x"].shape and u.shape == fx["sol_u"].shape
+  sol = node.optimizer.solve()
+  assert abs(sol["cost"] - float(fx["sol_cost"])) <= 5e-5 * abs(float(fx["sol_cost"]))
