@@ -46,6 +46,9 @@ enum {
   MYR_SYS_GLUCOSE = 7,
   MYR_SYS_HARVEST = 8,
   MYR_SYS_TIMBERHARVEST = 9,
+  MYR_SYS_SEIR = 10,
+  MYR_SYS_EPIDEMICSEIRN = 11,
+  MYR_SYS_HIVTREATMENT = 12,
   /* NodeSystem (myriad/systems/neural_ode/node_system.py:14-42) wrapping true system k: id = MYR_SYS_NODE_BASE + k.
    * Dynamics = the NODE MLP of myriad/neural_ode/create_node.py:110-117 (weights in MyrDesc.theta); cost, bounds,
    * horizon and the verification rollout are the true system's. */
@@ -116,7 +119,7 @@ typedef struct MyrIpmOpts {
   int32_t max_iter;        /* hp.max_iter (myriad/config.py:70); default 1000 */
   int32_t max_ls;          /* backtracking steps; default 40 */
   int32_t acceptable_iter; /* default 15 */
-  int32_t reserved;
+  int32_t max_soc;         /* second-order-correction attempts per iteration; 0 => default 4, negative => none */
   double tol;              /* default 1e-8 */
   double acceptable_tol;   /* default 1e-6 */
   double mu_init;          /* default 0.1 */

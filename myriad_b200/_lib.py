@@ -17,7 +17,7 @@ NODE_BASE = 100
 
 SYSTEM_IDS = {
   "SIMPLECASE": 0, "CARTPOLE": 1, "VANDERPOL": 2, "CANCERTREATMENT": 3, "MOULDFUNGICIDE": 4, "BIOREACTOR": 5,
-  "SIMPLECASEWITHBOUNDS": 6, "GLUCOSE": 7, "HARVEST": 8, "TIMBERHARVEST": 9,
+  "SIMPLECASEWITHBOUNDS": 6, "GLUCOSE": 7, "HARVEST": 8, "TIMBERHARVEST": 9, "SEIR": 10, "EPIDEMICSEIRN": 11, "HIVTREATMENT": 12,
 }
 OPT_SHOOTING, OPT_TRAPEZOIDAL, OPT_HERMITE_SIMPSON = 0, 1, 2
 METHOD_IDS = {"EULER": 0, "HEUN": 1, "MIDPOINT": 2, "RK4": 3}
@@ -44,7 +44,7 @@ class MyrSizes(C.Structure):
 
 
 class MyrIpmOpts(C.Structure):
-  _fields_ = [("max_iter", C.c_int32), ("max_ls", C.c_int32), ("acceptable_iter", C.c_int32), ("reserved", C.c_int32),
+  _fields_ = [("max_iter", C.c_int32), ("max_ls", C.c_int32), ("acceptable_iter", C.c_int32), ("max_soc", C.c_int32),
               ("tol", C.c_double), ("acceptable_tol", C.c_double), ("mu_init", C.c_double)]
 
 

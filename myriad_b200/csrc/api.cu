@@ -27,6 +27,9 @@ double system_default_T(int id) {
     case MYR_SYS_GLUCOSE: return 0.2;
     case MYR_SYS_HARVEST: return 10.0;
     case MYR_SYS_TIMBERHARVEST: return 5.0;
+    case MYR_SYS_SEIR: return 20.0;
+    case MYR_SYS_EPIDEMICSEIRN: return 20.0;
+    case MYR_SYS_HIVTREATMENT: return 20.0;
     default: return 1.0;
   }
 }

@@ -22,7 +22,7 @@ struct IpmOpts {
   double eta, rho;
   double delta_reg;   // tiny primal regularisation of the node blocks, removed again by iterative refinement
   int max_refine;
-  int reserved2;
+  int max_soc;        // second-order correction attempts when the first trial step is rejected (IPOPT max_soc = 4)
 };
 
 enum Status : int { ST_SOLVED = 0, ST_ACCEPTABLE = 1, ST_MAXITER = -1, ST_LINESEARCH = -2, ST_INERTIA = -3, ST_NAN = -13 };
@@ -53,7 +53,7 @@ struct Layout {
   int ldq, lds;   // leading dimensions of the element-major node / stage arrays
   int G, F, W, Hinv, gl, phi, psi, rb, dz, dzL, dzU, c, dlam;
   int crD, crU, crVL, crVU, crb, crx;
-  int lbr, ubr, rsl, rsu;
+  int lbr, ubr, rsl, rsu, zt, dz2, sch, ct, csoc, dl2;
   int dynf, dynJ, dynH;   // NODE systems: per-node MLP dynamics values / Jacobians / contracted Hessians
   int ext;
   int total;
@@ -83,6 +83,12 @@ struct Layout {
     crx = dlam;  // CR writes its solution straight into dlam
     lbr = o; o += ldq * S::NW;   // relaxed bounds per variable (-inf / +inf: none)
     ubr = o; o += ldq * S::NW;
+    zt = o; o += ldq * S::NW;    // trial point of the line search (reference layout, nv <= Q * NW)
+    dz2 = o; o += ldq * S::NW;   // second-order-correction step
+    sch = o; o += lds * S::NC;   // -J Hinv rb per stage (kept from the last KKT solve for re-solves)
+    ct = o; o += lds * S::NC;    // constraints at the trial point
+    csoc = o; o += lds * S::NC;  // accumulated SOC right-hand side
+    dl2 = o; o += lds * S::NC;   // multiplier step of the SOC solve
     rsl = o; o += ldq * S::NW;   // reciprocal slacks 1 / (x - lbr), 1 / (ubr - x) of the current iterate
     rsu = o; o += ldq * S::NW;
     dynf = dynJ = dynH = o;
@@ -426,7 +432,7 @@ MYR_HDI void block_cr_solve(int St, int ld, double* D, double* U, double* VL, do
 // the elimination of e from its surviving neighbours is  b_i -= VL_e^T b_e  (right neighbour e = i+s) and
 // b_i -= VU_e^T b_e (left neighbour e = i-s), which only needs data of already-final eliminated nodes.
 template <int NC>
-MYR_HDI void block_cr_resolve(int St, int ld, const double* D, const double* VL, const double* VU, double* b, double* x) {
+MYR_HDN void block_cr_resolve(int St, int ld, const double* D, const double* VL, const double* VU, double* b, double* x) {
   int s = 1;
   for (; s < St; s <<= 1) {
     for (int i = 2 * MYR_TID * s; i < St; i += 2 * MYR_NT * s) {
@@ -600,7 +606,7 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
 #pragma unroll
       for (int c2 = 0; c2 < NC; ++c2) D[(r * NC + c2) * ld + j] = 0.5 * (Dj[r * NC + c2] + Dj[c2 * NC + r]);
 #pragma unroll
-    for (int r = 0; r < NC; ++r) bb[r * ld + j] = bj[r];
+    for (int r = 0; r < NC; ++r) { bb[r * ld + j] = bj[r]; NS(sch, j, r) = bj[r] - NS(c, j, r); }
   }
   MYR_SYNC();
   MYR_KPH(7);
@@ -767,6 +773,51 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
   return ok;
 }
 
+// Second-order-correction solve (IPOPT A-5.5 ff.) with the factors the last kkt_solve left behind: same matrix,
+// constraint right-hand side csoc instead of c.   S dl2 = csoc - J Hinv rb,   dz2 = -Hinv (rb + J^T dl2).
+template <class S>
+MYR_HDN void kkt_soc_solve(const Problem& P, const Layout<S>& L, double* w, double* cr) {
+  constexpr int NW = S::NW, NC = S::NC;
+  const int Q = L.Q, St = L.St, ld = L.lds;
+  double* D = cr; double* VL = D + 2 * ld * NC * NC; double* VU = VL + ld * NC * NC;
+  double* bb = VU + ld * NC * NC;
+  for (int j = MYR_TID; j < St; j += MYR_NT)
+#pragma unroll
+    for (int r = 0; r < NC; ++r) bb[r * ld + j] = NS(csoc, j, r) + NS(sch, j, r);
+  MYR_SYNC();
+  block_cr_resolve<NC>(St, ld, D, VL, VU, bb, w + L.dl2);
+  for (int q = MYR_TID; q < Q; q += MYR_NT) {
+    double v[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) v[i] = NQ(rb, q, i);
+    const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
+    if (jp >= 0) {
+#pragma unroll
+      for (int r = 0; r < NC; ++r) {
+        const double d = NS(dl2, jp, r);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) v[i] += NQ(G, q, r * NW + i) * d;
+      }
+    }
+    if (js >= 0) {
+#pragma unroll
+      for (int r = 0; r < NC; ++r) {
+        const double d = NS(dl2, js, r);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) v[i] += NQ(F, q, r * NW + i) * d;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) a += NQ(Hinv, q, i * NW + k) * v[k];
+      NQ(dz2, q, i) = -a;
+    }
+  }
+  MYR_SYNC();
+}
+
 // ------------------------------------------------------------------ K3: interior-point solve of one instance
 struct IpmIO {
   const double* z0;   // [B][nvars] initial guess (reference layout)
@@ -848,7 +899,8 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
 #ifdef MYR_COUNT_KKT
   int n_kkt = 0;
 #endif
-  int it = 0, status = ST_MAXITER, n_acceptable = 0;
+  int it = 0, status = ST_MAXITER, n_acceptable = 0, hard_iters = 0;
+  bool soc_armed = false;
   double f = 0.0, E0 = INFINITY, cinf = INFINITY, c1 = 0.0;
   const double mu_floor = fmax(O.mu_min, O.tol / 10.0);
 
@@ -1025,9 +1077,33 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     const double phi0 = f - mu * slog + nu * c1;
     double alpha = a_pr;
     bool accepted = false;
-    double* zt = w + L.Hinv;  // Hinv is dead after kkt_solve: reuse as the trial point (reference layout needs nv <= Q*NW*NW)
+    double* zt = w + L.zt;
     double f_t = 0.0;
-    for (int ls = 0; ls < O.max_ls; ++ls) {
+    // Armijo with IPOPT's rounding-error relaxation (10 eps |phi|) so that converged iterates are not rejected by cancellation
+    const double armijo_slack = 10.0 * 2.220446049250313e-16 * fabs(phi0);
+    // One loop serves the backtracking trials (soc == false: step dz, length alpha) and the second-order-correction
+    // trials (soc == true: step dz2 from kkt_soc_solve, length a2), so the trial evaluation exists once in the code.
+    int ls = 0, ks = 0, ls_used = 0;
+    bool soc = false;
+    double a2 = 1.0, c1_prev = 0.0;
+    while (ls < O.max_ls) {
+      if (soc) {
+        kkt_soc_solve<S>(P, L, w, cr);
+        double m2 = 0.0;
+        for (int q = MYR_TID; q < Q; q += MYR_NT) {
+#pragma unroll 1
+          for (int i = 0; i < NW; ++i) {
+            const double d = NQ(dz2, q, i);
+            m2 = fmax(m2, fmax(-d * NQ(rsl, q, i), d * NQ(rsu, q, i)));
+          }
+        }
+        m2 = block_max(m2, red);
+        a2 = m2 > tau ? tau / m2 : 1.0;
+      }
+      const double a = soc ? a2 : alpha;
+      const int step_off = soc ? L.dz2 : L.dz;
+      ls_used = ls;
+      // ---- trial point z + a * step, its barrier log-sum, objective and constraints
       double blog = 0.0;
       for (int q = MYR_TID; q < Q; q += MYR_NT) {
         const uint32_t fm = fix_sh[q];
@@ -1035,7 +1111,7 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
 #pragma unroll 1
         for (int i = 0; i < NW; ++i) {
           const int id = S::zidx(P, q, i);
-          const double x = z[id] + alpha * NQ(dz, q, i);
+          const double x = z[id] + a * w[step_off + i * L.ldq + q];
           zt[id] = x;
           if (!((fm >> i) & 1u)) {
             const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i);
@@ -1048,13 +1124,44 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       MYR_SYNC();
       f_t = eval_nodes<S, 0>(P, L, zt, lam, w, red, mlp_scr);
       double ci_t, c1_t;
-      stage_constraints<S>(P, L, w, w + L.crb /*scratch*/, red, ci_t, c1_t);
+      stage_constraints<S>(P, L, w, w + L.ct, red, ci_t, c1_t);
       blog = block_sum(blog, red);
       const double phit = f_t - mu * blog + nu * c1_t;
-      // Armijo with IPOPT's rounding-error relaxation (10 eps |phi|) so that converged iterates are not rejected by cancellation
-      if (isfinite(phit) && phit <= phi0 + O.eta * alpha * Dm + 10.0 * 2.220446049250313e-16 * fabs(phi0)) { accepted = true; break; }
-      alpha *= 0.5;
+      if (isfinite(phit) && phit <= phi0 + O.eta * alpha * Dm + armijo_slack) { accepted = true; break; }
+      if (!soc) {
+        // second-order correction (IPOPT A-5.5 .. A-5.9): the full step was rejected without reducing the infeasibility,
+        // typically because the constraint curvature along dz outweighs the predicted decrease (Maratos effect).
+        // Re-solve with the same factors and the constraint right-hand side  alpha c + c(z + alpha dz).
+        // It is armed per instance only after two consecutive iterations that needed >= 4 step halvings: on the well
+        // behaved instances (the bulk of a batch) an unconditional SOC costs more re-solves than it saves iterations
+        // (CARTPOLE N=100: -12 % iterations, +16 % time), on the hard ones it is what makes the method converge.
+        if (ls == 0 && soc_armed && O.max_soc > 0 && c1_t >= c1) {
+          for (int j = MYR_TID; j < St; j += MYR_NT)
+#pragma unroll
+            for (int r = 0; r < NC; ++r) NS(csoc, j, r) = alpha * NS(c, j, r) + NS(ct, j, r);
+          MYR_SYNC();
+          soc = true; ks = 0; c1_prev = c1_t;
+          continue;
+        }
+        alpha *= 0.5; ++ls;
+      } else {
+        // kappa_soc: the correction must keep reducing the infeasibility, at most max_soc times
+        if (!(c1_t <= 0.99 * c1_prev) || ++ks >= O.max_soc) { soc = false; alpha *= 0.5; ++ls; continue; }
+        c1_prev = c1_t;
+        for (int j = MYR_TID; j < St; j += MYR_NT)
+#pragma unroll
+          for (int r = 0; r < NC; ++r) NS(csoc, j, r) = a2 * NS(csoc, j, r) + NS(ct, j, r);
+        MYR_SYNC();
+      }
     }
+    if (accepted && soc) {  // the multiplier step of the corrected system goes with the corrected primal step
+      for (int j = MYR_TID; j < St; j += MYR_NT)
+#pragma unroll
+        for (int r = 0; r < NC; ++r) NS(dlam, j, r) = NS(dl2, j, r);
+      alpha = a2;
+    }
+    hard_iters = ls_used >= 4 ? hard_iters + 1 : 0;
+    if (hard_iters >= 2) soc_armed = true;
     if (!accepted) { status = (E0 <= O.acceptable_tol) ? ST_ACCEPTABLE : ST_LINESEARCH; break; }
 
     MYR_PH(5);

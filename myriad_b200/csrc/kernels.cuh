@@ -470,7 +470,7 @@ __host__ __device__ inline void kkt_instance(const Problem& P, int b, const doub
 // shared-memory carve-up shared by the KKT and IPM kernels
 template <class S>
 struct SmemPlan {
-  size_t red, sig, fix, cr, total;
+  size_t red, sig, fix, cr, mlp, total;
   bool cr_in_smem;
   explicit SmemPlan(const Problem& P, size_t budget = 200 * 1024) {
     const Layout<S> L(P);
@@ -479,11 +479,10 @@ struct SmemPlan {
     fix = (((size_t)L.Q * sizeof(uint32_t)) + 15) & ~(size_t)15;
     cr = (size_t)L.cr_doubles() * sizeof(double);
     cr_in_smem = red + sig + fix + cr <= budget;
-    // the MLP pass's scratch (NODE systems) aliases the CR scratch: the two are never live at the same time
-    const size_t mlp = Layout<S>::kCoopMlp ? (size_t)mlp_scratch_doubles<S>(P.mlp) * sizeof(double) : 0;
-    size_t scratch = cr_in_smem ? cr : 0;
-    if (mlp > scratch) scratch = mlp;
-    total = red + sig + fix + scratch;
+    // the MLP pass's scratch (NODE systems) sits behind the CR scratch: the CR factors must survive the line-search
+    // evaluations (second-order-correction re-solves)
+    mlp = Layout<S>::kCoopMlp ? (size_t)mlp_scratch_doubles<S>(P.mlp) * sizeof(double) : 0;
+    total = red + sig + fix + (cr_in_smem ? cr : 0) + mlp;
   }
 };
 
@@ -554,8 +553,10 @@ inline IpmOpts make_opts(const MyrIpmOpts* o) {
   r.kappa_w_minus = 1.0 / 3.0; r.kappa_w_plus = 8.0; r.kappa_w_plus_first = 100.0;
   r.eta = 1e-4; r.rho = 0.1;
   r.delta_reg = 1e-8; r.max_refine = 1;
+  r.max_soc = (o && o->max_soc != 0) ? (o->max_soc > 0 ? o->max_soc : 0) : 4;
   if (const char* e = getenv("MYR_DELTA_REG")) r.delta_reg = atof(e);      // tuning knobs (debug)
   if (const char* e = getenv("MYR_MAX_REFINE")) r.max_refine = atoi(e);
+  if (const char* e = getenv("MYR_MAX_SOC")) r.max_soc = atoi(e) > 0 ? atoi(e) : 0;
   return r;
 }
 
@@ -585,7 +586,7 @@ __global__ void __launch_bounds__(IpmLaunch<S>::kThreads, IpmLaunch<S>::kMinBloc
   double* crs = reinterpret_cast<double*>(reinterpret_cast<char*>(fix) + ((((size_t)L.Q * sizeof(uint32_t)) + 15) & ~(size_t)15));
   for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
     double* cr = cr_in_smem ? crs : io.work + (long long)b * io.work_stride + L.crD;
-    ipm_solve_entry<S>(P, O, io, b, cr, red, sig, fix, crs);
+    ipm_solve_entry<S>(P, O, io, b, cr, red, sig, fix, cr_in_smem ? crs + L.cr_doubles() : crs);
     __syncthreads();
   }
 }

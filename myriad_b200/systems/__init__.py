@@ -99,6 +99,35 @@ class TimberHarvest(FiniteHorizonControlSystem):
                      terminal_cost=False, discrete=False, device_name="TIMBERHARVEST", params=[r, k])
 
 
+class SEIR(FiniteHorizonControlSystem):
+  """myriad/systems/miscellaneous/seir.py:47-95 (parameters are fixed in the reference's constructor)"""
+
+  def __init__(self):
+    self.b, self.d, self.c, self.e, self.g, self.a, self.A = 0.525, 0.5, 0.0001, 0.5, 0.1, 0.2, 0.1
+    super().__init__(x_0=np.array([1000.0, 100.0, 50.0, 1000.0 + 100.0 + 50.0 + 15.0]), x_T=None, T=20,
+                     bounds=np.array([[0., 2000.], [0., 250.], [0., 250.], [0., 3000.], [0., 1.]]), terminal_cost=False,
+                     device_name="SEIR", params=[self.A, self.b, self.d, self.c, self.e, self.g, self.a])
+
+
+class EpidemicSEIRN(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/epidemic_seirn.py:43-95"""
+
+  def __init__(self, A=.1, b=.525, d=.5, c=.0001, e=.5, g=.1, a=.2, x_0=(1000., 100., 50., 15.), T=20.):
+    inf = np.inf
+    super().__init__(x_0=np.array([x_0[0], x_0[1], x_0[2], float(np.sum(np.asarray(x_0)))]), x_T=None, T=T,
+                     bounds=np.array([[-inf, inf], [-inf, inf], [-inf, inf], [-inf, inf], [0., 0.9]]), terminal_cost=False,
+                     discrete=False, device_name="EPIDEMICSEIRN", params=[A, b, d, c, e, g, a])
+
+
+class HIVTreatment(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/hiv_treatment.py:33-111"""
+
+  def __init__(self, s=10., m_1=.02, m_2=.5, m_3=4.4, r=.03, T_max=1500., k=.000024, N=300., x_0=(800., .04, 1.5), A=.05, T=20.):
+    super().__init__(x_0=np.array([x_0[0], x_0[1], x_0[2]], dtype=np.float64), x_T=None, T=T,
+                     bounds=np.array([[0., 1600.], [0., 100.], [0., 100.], [0., 1.]]), terminal_cost=False, discrete=False,
+                     device_name="HIVTREATMENT", params=[s, m_1, m_2, m_3, r, T_max, k, N, A])
+
+
 class NodeSystem(FiniteHorizonControlSystem):
   """myriad/systems/neural_ode/node_system.py:14-42: a system whose (parametrized) dynamics is the neural-ODE MLP of
   myriad/neural_ode/create_node.py:110-117 applied to concat(x, u), while cost, bounds, horizon, start/end states and
@@ -168,7 +197,7 @@ class SystemType(Enum):
   """Same member names as the reference enum; members without a device implementation raise on call."""
   CARTPOLE = CartPole
   VANDERPOL = VanDerPol
-  SEIR = _NotOnDevice("SEIR")
+  SEIR = SEIR
   TUMOUR = _NotOnDevice("TUMOUR")
   MOUNTAINCAR = _NotOnDevice("MOUNTAINCAR")
   PENDULUM = _NotOnDevice("PENDULUM")
@@ -177,9 +206,9 @@ class SystemType(Enum):
   BACTERIA = _NotOnDevice("BACTERIA")
   SIMPLECASEWITHBOUNDS = SimpleCaseWithBounds
   CANCERTREATMENT = CancerTreatment
-  EPIDEMICSEIRN = _NotOnDevice("EPIDEMICSEIRN")
+  EPIDEMICSEIRN = EpidemicSEIRN
   HARVEST = Harvest
-  HIVTREATMENT = _NotOnDevice("HIVTREATMENT")
+  HIVTREATMENT = HIVTreatment
   BEARPOPULATIONS = _NotOnDevice("BEARPOPULATIONS")
   GLUCOSE = Glucose
   TIMBERHARVEST = TimberHarvest

@@ -226,6 +226,55 @@ class TimberHarvest(OracleSystem):
     return -e * x[..., 0] * (1 - u[..., 0])  # timber_harvest.py:85
 
 
+class SEIR(OracleSystem):
+  """myriad/systems/miscellaneous/seir.py:47-95"""
+
+  def __init__(self, A=0.1, b=0.525, d=0.5, c=0.0001, e=0.5, g=0.1, a=0.2):
+    super().__init__("SEIR", np.array([1000.0, 100.0, 50.0, 1165.0]), None, 20,
+                     np.array([[0., 2000.], [0., 250.], [0., 250.], [0., 3000.], [0., 1.]]), False,
+                     dict(A=A, b=b, d=d, c=c, e=e, g=g, a=a))
+
+  def dynamics(self, x, u):
+    p = self.params
+    S_, E_, I_, N_ = x[..., 0], x[..., 1], x[..., 2], x[..., 3]
+    u0 = u[..., 0]
+    return _stack([p["b"] * N_ - p["d"] * S_ - p["c"] * S_ * I_ - u0 * S_,       # seir.py:86
+                   p["c"] * S_ * I_ - (p["e"] + p["d"]) * E_,                   # :87
+                   p["e"] * E_ - (p["g"] + p["a"] + p["d"]) * I_,               # :88
+                   (p["b"] - p["d"]) * N_ - p["a"] * I_], x)                    # :89
+
+  def cost(self, x, u, t):
+    return self.params["A"] * x[..., 2] + u[..., 0] ** 2  # seir.py:95
+
+
+class EpidemicSEIRN(SEIR):
+  """myriad/systems/lenhart/epidemic_seirn.py:43-95: same vector field, unbounded states, u in [0, 0.9]"""
+
+  def __init__(self, A=.1, b=.525, d=.5, c=.0001, e=.5, g=.1, a=.2, x_0=(1000., 100., 50., 15.), T=20.):
+    OracleSystem.__init__(self, "EPIDEMICSEIRN", np.array([x_0[0], x_0[1], x_0[2], float(np.sum(x_0))]), None, T,
+                          np.array([[-np.inf, np.inf]] * 4 + [[0., 0.9]]), False, dict(A=A, b=b, d=d, c=c, e=e, g=g, a=a))
+
+
+class HIVTreatment(OracleSystem):
+  """myriad/systems/lenhart/hiv_treatment.py:33-111"""
+
+  def __init__(self, s=10., m_1=.02, m_2=.5, m_3=4.4, r=.03, T_max=1500., k=.000024, N=300., x_0=(800., .04, 1.5), A=.05, T=20.):
+    super().__init__("HIVTREATMENT", np.array([x_0[0], x_0[1], x_0[2]]), None, T,
+                     np.array([[0., 1600.], [0., 100.], [0., 100.], [0., 1.]]), False,
+                     dict(s=s, m_1=m_1, m_2=m_2, m_3=m_3, r=r, T_max=T_max, k=k, N=N, A=A))
+
+  def dynamics(self, x, u):
+    p = self.params
+    x0, x1, x2 = x[..., 0], x[..., 1], x[..., 2]
+    u0 = u[..., 0]
+    return _stack([p["s"] / (1 + x2) - p["m_1"] * x0 + p["r"] * x0 * (1 - (x0 + x1) / p["T_max"]) - u0 * p["k"] * x0 * x2,  # :79
+                   u0 * p["k"] * x0 * x2 - p["m_2"] * x1,                       # :80
+                   p["N"] * p["m_2"] * x1 - p["m_3"] * x2], x)                  # :81
+
+  def cost(self, x, u, t):
+    return -self.params["A"] * x[..., 0] + (1 - u[..., 0]) ** 2  # hiv_treatment.py:111
+
+
 class NodeSystem(OracleSystem):
   """NODE-dynamics wrapper: myriad/systems/neural_ode/node_system.py:14-42 with the MLP of
   myriad/neural_ode/create_node.py:110-117 (hk.Linear = x @ w + b, sigmoid between layers).
@@ -282,6 +331,9 @@ SYSTEMS = {
   "GLUCOSE": Glucose,
   "HARVEST": Harvest,
   "TIMBERHARVEST": TimberHarvest,
+  "SEIR": SEIR,
+  "EPIDEMICSEIRN": EpidemicSEIRN,
+  "HIVTREATMENT": HIVTreatment,
 }
 
 

@@ -129,6 +129,30 @@ def system_defs():
       lambda x, u, p: [p["k"] * x[0] * u[0]],
       lambda x, u, t, p: -sp.exp(-p["r"] * t) * x[0] * (1 - u[0]),
       ref="myriad/systems/lenhart/timber_harvest.py:62-85")
+
+  # myriad/systems/miscellaneous/seir.py:47-95 (state = S, E, I, N)
+  def seir_f(x, u, p):
+    S_, E_, I_, N_ = x
+    return [p["b"] * N_ - p["d"] * S_ - p["c"] * S_ * I_ - u[0] * S_,
+            p["c"] * S_ * I_ - (p["e"] + p["d"]) * E_,
+            p["e"] * E_ - (p["g"] + p["a"] + p["d"]) * I_,
+            (p["b"] - p["d"]) * N_ - p["a"] * I_]
+  seir_params = [("A", 0.1), ("b", 0.525), ("d", 0.5), ("c", 0.0001), ("e", 0.5), ("g", 0.1), ("a", 0.2)]
+  add("SEIR", 10, 4, 1, seir_params, seir_f, lambda x, u, t, p: p["A"] * x[2] + u[0] ** 2,
+      ref="myriad/systems/miscellaneous/seir.py:83-95")
+
+  # myriad/systems/lenhart/epidemic_seirn.py:81-95 (same vector field, different bounds / constructor)
+  add("EPIDEMICSEIRN", 11, 4, 1, seir_params, seir_f, lambda x, u, t, p: p["A"] * x[2] + u[0] ** 2,
+      ref="myriad/systems/lenhart/epidemic_seirn.py:81-95")
+
+  # myriad/systems/lenhart/hiv_treatment.py:74-111
+  add("HIVTREATMENT", 12, 3, 1,
+      [("s", 10.0), ("m_1", 0.02), ("m_2", 0.5), ("m_3", 4.4), ("r", 0.03), ("T_max", 1500.0), ("k", 0.000024), ("N", 300.0), ("A", 0.05)],
+      lambda x, u, p: [p["s"] / (1 + x[2]) - p["m_1"] * x[0] + p["r"] * x[0] * (1 - (x[0] + x[1]) / p["T_max"]) - u[0] * p["k"] * x[0] * x[2],
+                       u[0] * p["k"] * x[0] * x[2] - p["m_2"] * x[1],
+                       p["N"] * p["m_2"] * x[1] - p["m_3"] * x[2]],
+      lambda x, u, t, p: -p["A"] * x[0] + (1 - u[0]) ** 2,
+      ref="myriad/systems/lenhart/hiv_treatment.py:74-111")
   return S
 
 
