@@ -265,8 +265,21 @@ __host__ __device__ inline void eval_instance(const Problem& P, int b, const dou
 // Device K1: one CTA per instance, one thread per node.  Node blocks of the Jacobian are staged in shared memory
 // (rows padded by one double against bank conflicts) and written out with fully coalesced stores -- the Jacobian is
 // 74% of the kernel's HBM traffic; z (read) and grad (write) are accessed as 32-byte-per-thread runs directly.
+// Launch shape of K1: the kernel is bound by the latency of its own loads and store drain, so resident CTAs are what
+// matters -- two-node-per-stage schemes run 128 threads with registers capped for MYR_K1_MINBLOCKS CTAs per SM.
+#ifndef MYR_K1_MINBLOCKS
+#define MYR_K1_MINBLOCKS 5
+#endif
 template <class S>
-__global__ void __launch_bounds__(256) eval_kernel(Problem P, const double* __restrict__ z_all, const double* __restrict__ lam_all,
+struct EvalLaunch {
+  static constexpr bool kWide = Layout<S>::kCoopMlp || S::kMaxStageNodes >= 3;
+  static constexpr int kThreads = kWide ? 256 : 128;
+  static constexpr int kMinBlocks = kWide ? 1 : MYR_K1_MINBLOCKS;
+  static int threads(int Q) { const int t = threads_for(Q, Layout<S>::kCoopMlp); return t < kThreads ? t : kThreads; }
+};
+
+template <class S>
+__global__ void __launch_bounds__(EvalLaunch<S>::kThreads, EvalLaunch<S>::kMinBlocks) eval_kernel(Problem P, const double* __restrict__ z_all, const double* __restrict__ lam_all,
                                                    double* __restrict__ f_out, double* __restrict__ grad_out, double* __restrict__ c_out,
                                                    double* __restrict__ J_out, double* __restrict__ H_out) {
   extern __shared__ __align__(16) double smem[];
@@ -398,7 +411,7 @@ int sys_eval(const MyrDesc* desc, int B, const double* z, const double* lam, dou
     const size_t sm = smd * sizeof(double);
     if (sm > 200 * 1024) return fail(MYR_E_UNSUPPORTED, "problem too large for the shared-memory staged K1 (%s%lld bytes)", "", (long long)sm);
     if (sm > 48 * 1024) cudaFuncSetAttribute(eval_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    eval_kernel<S><<<B, threads_for(L.Q, Layout<S>::kCoopMlp), sm, (cudaStream_t)stream>>>(P, z, lam, f, grad, c, Jblk, Hblk);
+    eval_kernel<S><<<B, EvalLaunch<S>::threads(L.Q), sm, (cudaStream_t)stream>>>(P, z, lam, f, grad, c, Jblk, Hblk);
     return cuda_check("myr_eval");
   });
 }

@@ -260,7 +260,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const doubl
       for (int mt = warp; mt < MT; mt += nwarp) {
         const int o = 8 * mt + g;
         double c0 = o < out ? b[o] : 0.0, c1 = c0;
-        for (int ks = 0; ks < KS; ++ks) {
+        _Pragma("unroll 4") for (int ks = 0; ks < KS; ++ks) {
           const int i = 4 * ks + t;
           const double a = (i < in && o < out) ? __ldg(w + i * out + o) : 0.0;
           dmma_m8n8k4(c0, c1, a, Bs[i * 8 + g]);
@@ -279,7 +279,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const doubl
       for (int mt = warp; mt < MT; mt += nwarp) {
         const int o = 8 * mt + g;
         double c0 = o < n ? b[o] : 0.0, c1 = c0;
-        for (int ks = 0; ks < KS; ++ks) {
+        _Pragma("unroll 4") for (int ks = 0; ks < KS; ++ks) {
           const int i = 4 * ks + t;
           const double a = (i < in && o < n) ? __ldg(w + i * n + o) : 0.0;
           dmma_m8n8k4(c0, c1, a, Bs[i * 8 + g]);
@@ -302,7 +302,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const doubl
         for (int mt = warp; mt < MT; mt += nwarp) {
           const int i = 8 * mt + g;
           double c0 = 0.0, c1 = 0.0;
-          for (int ks = 0; ks < KS; ++ks) {
+          _Pragma("unroll 4") for (int ks = 0; ks < KS; ++ks) {
             const int o = 4 * ks + t;
             const double a = (i < rows && o < k) ? __ldg(w + i * k + o) : 0.0;
             dmma_m8n8k4(c0, c1, a, Bs[o * 8 + g]);
@@ -340,7 +340,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const doubl
           } else {
 #pragma unroll
             for (int i = 0; i < NW; ++i) { c[r][i][0] = 0.0; c[r][i][1] = 0.0; }
-            for (int ks = 0; ks < KS; ++ks) {
+            _Pragma("unroll 4") for (int ks = 0; ks < KS; ++ks) {
               const int k = 4 * ks + t;
               const double a = (k < in && o < out) ? __ldg(w + k * out + o) : 0.0;
 #pragma unroll
@@ -386,7 +386,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const doubl
         double c[NW][2];
 #pragma unroll
         for (int i = 0; i < NW; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
-        for (int ks = 0; ks < KS; ++ks) {
+        _Pragma("unroll 4") for (int ks = 0; ks < KS; ++ks) {
           const int k = 4 * ks + t;
           const double a = (k < in && o < n) ? __ldg(w + k * n + o) : 0.0;
 #pragma unroll
