@@ -119,3 +119,35 @@ def test_two_rank_shard_and_gather_gloo():
   np.testing.assert_array_equal(got[:, :s.nvars], out["z"])
   np.testing.assert_array_equal(got[:, -2], out["status"].astype(np.float64))
   assert (out["status"] == 0).all()
+
+
+def test_node_system_surface_and_descriptor():
+  """NodeSystem (node_system.py:14-42): true system's data, MLP layers parsed from haiku-style parameters in layer order
+  (create_node.py:124-131), flattened weight vector and descriptor fields of the C ABI; no GPU involved."""
+  from myriad_b200 import _lib as ML, problems as PR
+  from myriad_b200.neural_ode import NeuralODE, init_params
+  from myriad_b200.config import Config, HParams, OptimizerType
+  from myriad_b200.systems import NodeSystem, SystemType, mlp_layers
+  true = SystemType.CARTPOLE()
+  params = init_params(5, (7, 9), 4, seed=1)
+  ns = NodeSystem(params, true)
+  assert ns.device_name == "NODE_CARTPOLE" and ns.hidden == [7, 9] and ns.T == true.T and np.array_equal(ns.bounds, true.bounds)
+  assert ns.theta.size == 5 * 7 + 7 + 7 * 9 + 9 + 9 * 4 + 4
+  np.testing.assert_array_equal(ns.theta[:35], params["linear"]["w"].ravel())
+  np.testing.assert_array_equal(ns.theta[-4:], params["linear_2"]["b"])
+  flat = {f"{k}/{p}": v for k, d in params.items() for p, v in d.items()}  # .npz style keys load as well
+  assert [w.shape for w, _ in mlp_layers(flat)] == [(5, 7), (7, 9), (9, 4)]
+  with pytest.raises(ValueError):
+    NodeSystem(init_params(4, (8,), 4), true)  # wrong input width
+  d = PR.Transcription(ns, PR.TRAPEZOIDAL, "HEUN", 10, 1).desc(device="host")
+  assert d.system_id == ML.NODE_BASE + ML.SYSTEM_IDS["CARTPOLE"] and d.node_num_hidden == 2 and list(d.node_hidden[:2]) == [7, 9]
+  assert d.theta_doubles == ns.theta.size
+  s = ML.problem_sizes(d)
+  assert (s.n, s.m, s.nvars, s.ncon) == (4, 1, 55, 40)
+  d.theta_doubles += 1  # inconsistent sizes are an argument error, not a crash
+  with pytest.raises(KeyError):
+    ML.problem_sizes(d)
+  hp = HParams(system=SystemType.CARTPOLE, optimizer=OptimizerType.COLLOCATION, intervals=10, hidden_layers=(7, 9))
+  node = NeuralODE(hp, Config(verbose=False, plot=False), params=params)
+  y = node.apply(params, np.zeros(5))
+  assert y.shape == (4,)
