@@ -30,6 +30,8 @@ double system_default_T(int id) {
     case MYR_SYS_SEIR: return 20.0;
     case MYR_SYS_EPIDEMICSEIRN: return 20.0;
     case MYR_SYS_HIVTREATMENT: return 20.0;
+    case MYR_SYS_BACTERIA: return 1.0;
+    case MYR_SYS_TUMOUR: return 1.2;
     default: return 1.0;
   }
 }

@@ -1282,9 +1282,15 @@ ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, doub
       if (rr >= 0) { z[rr] = zI[q * NW + i]; zL[rr] = zLI[q * NW + i]; zU[rr] = zUI[q * NW + i]; }
     }
   }
+  // the lifted NLP puts a terminal cost tc . s_G on the last shooting node itself, the reference's objective puts it on
+  // the rollout end px_{K-1} (shooting.py:205-208): same optimum, but the multiplier of the last block differs by tc
+  double tcoef[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) tcoef[i] = 0.0;
+  if (S::System::has_terminal && P.terminal_cost) S::System::terminal_coef(P.p, tcoef);
   for (int k = MYR_TID; k < P.N; k += MYR_NT)
 #pragma unroll
-    for (int i = 0; i < n; ++i) lam[k * n + i] = lamI[((k + 1) * P.cpi - 1) * NC + i];
+    for (int i = 0; i < n; ++i) lam[k * n + i] = lamI[((k + 1) * P.cpi - 1) * NC + i] - (k == P.N - 1 ? tcoef[i] : 0.0);
   MYR_SYNC();
   // objective and constraint violation as the reference defines them (shooting.py:169-241)
   double fs = 0.0, cm = 0.0;

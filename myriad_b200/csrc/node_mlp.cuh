@@ -129,6 +129,8 @@ struct SysNode {
   static constexpr int id = 100 + True::id, n = True::n, m = True::m, nw = True::nw, np = True::np;
   static constexpr bool time_dependent_cost = True::time_dependent_cost;
   static constexpr bool kNode = true;
+  static constexpr bool has_terminal = True::has_terminal;
+  MYR_HD static void terminal_coef(const double* p, double* tc) { True::terminal_coef(p, tc); }
   static constexpr const char* name = True::name;  // reported as NODE(<name>)
   MYR_HD static void default_params(double* p) { True::default_params(p); }
   // true cost (node_system.py:41-42)

@@ -9,7 +9,7 @@
 namespace myr {
 
 struct RolloutArgs {
-  int B, num_steps, nu_rows, method;
+  int B, num_steps, nu_rows, method, terminal_cost;
   double h, T;
   double p[kMaxParams];
   const double* u;   // [B][nu_rows][m]
@@ -21,7 +21,7 @@ struct RolloutArgs {
 template <class Sys>
 static RolloutArgs make_rollout_args(const Problem& P, int num_steps, int nu_rows, const double* u, const double* x0, double* xs, double* cost) {
   RolloutArgs A;
-  A.B = P.B; A.num_steps = num_steps; A.nu_rows = nu_rows; A.method = P.method;
+  A.B = P.B; A.num_steps = num_steps; A.nu_rows = nu_rows; A.method = P.method; A.terminal_cost = P.terminal_cost;
   A.T = P.T; A.h = P.T / num_steps;
   for (int i = 0; i < kMaxParams; ++i) A.p[i] = P.p[i];
   A.u = u; A.x0 = x0; A.xs = xs; A.cost = cost;
@@ -101,7 +101,14 @@ MYR_HDI void rollout_instance(const RolloutArgs& A, int b) {
       for (int i = 0; i < n; ++i) xs[(idx + 1) * n + i] = x[i];
     }
   }
-  A.cost[b] = x[n];
+  double cst = x[n];
+  if (Sys::has_terminal && A.terminal_cost) {  // utils.py:294-295: + terminal_cost_fn(x(T), us[-1]), linear in x(T)
+    double tc[n];
+    Sys::terminal_coef(A.p, tc);
+#pragma unroll
+    for (int i = 0; i < n; ++i) cst += tc[i] * x[i];
+  }
+  A.cost[b] = cst;
 }
 
 }  // namespace myr

@@ -129,6 +129,16 @@ struct Trapezoid {
       phi[r] = has_phi ? hh * f[r] + v[r] : 0.0;
       psi[r] = has_psi ? hh * f[r] - v[r] : 0.0;
     }
+    // terminal cost on the last node: trapezoidal.py:126-127 (linear in x_T for every reference system: no Hessian term)
+    if (Sys::has_terminal && P.terminal_cost && q == P.N) {
+      double tc[n];
+      Sys::terminal_coef(P.p, tc);
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        ell += tc[i] * v[i];
+        if (MODE >= 1) gl[i] += tc[i];
+      }
+    }
   }
 };
 

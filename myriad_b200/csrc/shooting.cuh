@@ -105,7 +105,19 @@ struct ShootingLifted {
     ell = 0.0;
 #pragma unroll
     for (int r = 0; r < NC; ++r) phi[r] = 0.0;
-    if (!has_phi) return;
+    if (!has_phi) {
+      // last node: terminal cost on the end state of the last interval (shooting.py:205-208), linear in x_T
+      if (Sys::has_terminal && P.terminal_cost) {
+        double tc[n];
+        Sys::terminal_coef(P.p, tc);
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          ell += tc[i] * v[i];
+          if (MODE >= 1) gl[i] += tc[i];
+        }
+      }
+      return;
+    }
 
     // Butcher data per method.  a[c] = coefficient of the PREVIOUS call's k in x_c (all four schemes only chain one
     // call back), b[c] = weight of k_c in the update, tc[c] = time offset / h, control of call c = sum_s cu[c][s] u_slot_s
@@ -353,6 +365,20 @@ struct ShootingInterval {
     }
 #pragma unroll
     for (int i = 0; i < n; ++i) px[i] = s[i];
+    if (Sys::has_terminal && P.terminal_cost && k == P.N - 1) {  // shooting.py:205-208
+      double tc[n];
+      Sys::terminal_coef(P.p, tc);
+#pragma unroll
+      for (int i = 0; i < n; ++i) cost += tc[i] * s[i];
+      if (DERIV) {
+        for (int col = 0; col < ncol; ++col) {
+          double a = 0.0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) a += tc[i] * S[i * ncol + col];
+          S[n * ncol + col] += a;
+        }
+      }
+    }
   }
 };
 

@@ -128,6 +128,31 @@ class HIVTreatment(FiniteHorizonControlSystem):
                      device_name="HIVTREATMENT", params=[s, m_1, m_2, m_3, r, T_max, k, N, A])
 
 
+class Bacteria(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/bacteria.py:34-86 (terminal cost -C x(T))"""
+
+  def __init__(self, r=1., A=1., B=12., C=1., x_0=1.):
+    super().__init__(x_0=np.array([x_0], dtype=np.float64), x_T=None, T=1, bounds=np.array([[0., 10.], [0., 2.]]),
+                     terminal_cost=True, discrete=False, device_name="BACTERIA", params=[r, A, B, C])
+    self.r, self.A, self.B, self.C = r, A, B, C
+
+  def terminal_cost_fn(self, x_T, u_T, T=None):
+    return -self.C * np.squeeze(x_T)
+
+
+class Tumour(FiniteHorizonControlSystem):
+  """myriad/systems/miscellaneous/tumour.py:44-108 (no running cost; terminal cost p(T))"""
+
+  def __init__(self, xi=0.084, b=5.85, d=0.00873, G=0.15, mu=0.02):
+    p_ = q_ = ((b - mu) / d) ** (3 / 2)
+    super().__init__(x_0=np.array([p_ / 2, q_ / 4, 0.0]), x_T=None, T=1.2,
+                     bounds=np.array([[0., p_], [0., q_], [0., 15.], [0., 75.]]), terminal_cost=True,
+                     device_name="TUMOUR", params=[xi, b, d, G, mu])
+
+  def terminal_cost_fn(self, x_T, u_T, T=None):
+    return x_T[0]
+
+
 class NodeSystem(FiniteHorizonControlSystem):
   """myriad/systems/neural_ode/node_system.py:14-42: a system whose (parametrized) dynamics is the neural-ODE MLP of
   myriad/neural_ode/create_node.py:110-117 applied to concat(x, u), while cost, bounds, horizon, start/end states and
@@ -198,12 +223,12 @@ class SystemType(Enum):
   CARTPOLE = CartPole
   VANDERPOL = VanDerPol
   SEIR = SEIR
-  TUMOUR = _NotOnDevice("TUMOUR")
+  TUMOUR = Tumour
   MOUNTAINCAR = _NotOnDevice("MOUNTAINCAR")
   PENDULUM = _NotOnDevice("PENDULUM")
   SIMPLECASE = SimpleCase
   MOULDFUNGICIDE = MouldFungicide
-  BACTERIA = _NotOnDevice("BACTERIA")
+  BACTERIA = Bacteria
   SIMPLECASEWITHBOUNDS = SimpleCaseWithBounds
   CANCERTREATMENT = CancerTreatment
   EPIDEMICSEIRN = EpidemicSEIRN

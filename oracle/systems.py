@@ -275,6 +275,48 @@ class HIVTreatment(OracleSystem):
     return -self.params["A"] * x[..., 0] + (1 - u[..., 0]) ** 2  # hiv_treatment.py:111
 
 
+class Bacteria(OracleSystem):
+  """myriad/systems/lenhart/bacteria.py:34-86"""
+
+  def __init__(self, r=1., A=1., B=12., C=1., x_0=1.):
+    super().__init__("BACTERIA", np.array([x_0]), None, 1, np.array([[0., 10.], [0., 2.]]), True, dict(r=r, A=A, B=B, C=C))
+
+  def dynamics(self, x, u):
+    xp = _xp(x)
+    p = self.params
+    x0, u0 = x[..., 0], u[..., 0]
+    return _stack([p["r"] * x0 + p["A"] * u0 * x0 - p["B"] * u0 ** 2 * xp.exp(-x0)], x)  # bacteria.py:61
+
+  def cost(self, x, u, t):
+    return u[..., 0] ** 2  # bacteria.py:77
+
+  def terminal_cost_fn(self, x, u):
+    return -self.params["C"] * x[..., 0]  # bacteria.py:86
+
+
+class Tumour(OracleSystem):
+  """myriad/systems/miscellaneous/tumour.py:44-108"""
+
+  def __init__(self, xi=0.084, b=5.85, d=0.00873, G=0.15, mu=0.02):
+    p_ = ((b - mu) / d) ** (3 / 2)
+    super().__init__("TUMOUR", np.array([p_ / 2, p_ / 4, 0.0]), None, 1.2,
+                     np.array([[0., p_], [0., p_], [0., 15.], [0., 75.]]), True, dict(xi=xi, b=b, d=d, G=G, mu=mu))
+
+  def dynamics(self, x, u):
+    xp = _xp(x)
+    p = self.params
+    pp, q, u0 = x[..., 0], x[..., 1], u[..., 0]
+    return _stack([-p["xi"] * pp * xp.log(pp / q),                                             # tumour.py:79
+                   q * (p["b"] - (p["mu"] + p["d"] * pp ** (2 / 3) + p["G"] * u0)),            # :80
+                   u0 + 0 * pp], x)                                                            # :81
+
+  def cost(self, x, u, t):
+    return 0 * x[..., 0]  # tumour.py:98
+
+  def terminal_cost_fn(self, x, u):
+    return x[..., 0]  # tumour.py:106-108
+
+
 class NodeSystem(OracleSystem):
   """NODE-dynamics wrapper: myriad/systems/neural_ode/node_system.py:14-42 with the MLP of
   myriad/neural_ode/create_node.py:110-117 (hk.Linear = x @ w + b, sigmoid between layers).
@@ -334,6 +376,8 @@ SYSTEMS = {
   "SEIR": SEIR,
   "EPIDEMICSEIRN": EpidemicSEIRN,
   "HIVTREATMENT": HIVTreatment,
+  "BACTERIA": Bacteria,
+  "TUMOUR": Tumour,
 }
 
 

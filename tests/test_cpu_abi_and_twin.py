@@ -25,12 +25,10 @@ def ML():
 
 
 def _desc(ML, case):
-  sysname, opt, quad, meth, intervals, cpi = CASES[case]
-  if sysname.startswith("NODE_"):  # NodeSystem: MLP weights passed as a HOST pointer to the host twin
-    from tests.cases import product_transcription
-    return product_transcription(case).desc(device="host")
-  optid = ML.OPT_SHOOTING if opt == "SHOOTING" else (ML.OPT_TRAPEZOIDAL if quad == "TRAPEZOIDAL" else ML.OPT_HERMITE_SIMPSON)
-  return ML.make_desc(sysname, optid, meth, intervals, cpi)
+  # the descriptor the product builds for this case (system parameters, terminal-cost flag; for a NodeSystem the MLP
+  # weights are passed as a HOST pointer to the host twin)
+  from tests.cases import product_transcription
+  return product_transcription(case).desc(device="host")
 
 
 def p(a):
@@ -123,7 +121,7 @@ def test_host_twin_k1_matches_reference_fixture(ML, case):
   sysname, opt, quad, meth, K, cpi = CASES[case]
   f, grad, c, J, _ = _host_eval(ML, d, s, np.ascontiguousarray(np.stack([fx["z"], fx["guess"]])))
   np.testing.assert_allclose(f, [fx["obj_z"], fx["obj_guess"]], rtol=1e-12, atol=1e-14)
-  np.testing.assert_allclose(c, np.stack([fx["con_z"], fx["con_guess"]]), rtol=1e-12, atol=1e-13)
+  np.testing.assert_allclose(c, np.stack([fx["con_z"], fx["con_guess"]]), rtol=5e-12, atol=1e-13)  # pow() in TUMOUR: a few ulps
   np.testing.assert_allclose(grad[0], fx["grad_z"], rtol=1e-11, atol=1e-13)
   Jd = _dense_J_shooting(s, J[0], K, cpi, meth) if opt == "SHOOTING" else _dense_J(s, J[0], quad)
   np.testing.assert_allclose(Jd, fx["jac_z"], rtol=1e-11, atol=1e-13)

@@ -153,6 +153,21 @@ def system_defs():
                        p["N"] * p["m_2"] * x[1] - p["m_3"] * x[2]],
       lambda x, u, t, p: -p["A"] * x[0] + (1 - u[0]) ** 2,
       ref="myriad/systems/lenhart/hiv_treatment.py:74-111")
+  # myriad/systems/lenhart/bacteria.py:34-86 (terminal cost -C x(T))
+  add("BACTERIA", 13, 1, 1, [("r", 1.0), ("A", 1.0), ("B", 12.0), ("C", 1.0)],
+      lambda x, u, p: [p["r"] * x[0] + p["A"] * u[0] * x[0] - p["B"] * u[0] ** 2 * sp.exp(-x[0])],
+      lambda x, u, t, p: u[0] ** 2,
+      term=lambda x, u, p: -p["C"] * x[0],
+      ref="myriad/systems/lenhart/bacteria.py:59-86")
+
+  # myriad/systems/miscellaneous/tumour.py:44-108 (no running cost, terminal cost p(T))
+  add("TUMOUR", 14, 3, 1, [("xi", 0.084), ("b", 5.85), ("d", 0.00873), ("G", 0.15), ("mu", 0.02)],
+      lambda x, u, p: [-p["xi"] * x[0] * sp.log(x[0] / x[1]),
+                       x[1] * (p["b"] - (p["mu"] + p["d"] * x[0] ** sp.Rational(2, 3) + p["G"] * u[0])),
+                       u[0]],
+      lambda x, u, t, p: sp.Integer(0),
+      term=lambda x, u, p: x[0],
+      ref="myriad/systems/miscellaneous/tumour.py:77-108")
   return S
 
 
@@ -262,6 +277,24 @@ def gen_system(name, d):
             [("const double g_", g, "=")] + [(f"g[{j}]", gg[j], "=") for j in range(nw)] +
             [(f"H[{packed_index(i, j, nw)}]", wq * Hg[i][j], "+=") for i in range(nw) for j in range(i, nw)],
             ret="g_", pre=["    (void)t; (void)wq;"])
+  # terminal cost (systems/base.py:101-111): every reference system with terminal_cost=True has one that is LINEAR in
+  # x_T and independent of u_T (bacteria.py:84-86, tumour.py:106-108, predator_prey.py:120-122), so the device code
+  # carries only its coefficient vector: term(x_T) = sum_i tc[i] x_T[i]
+  tc = [sp.Integer(0)] * n
+  if d["term"] is not None:
+    term = sp.sympify(d["term"](x, u, psym))
+    tc = [sp.diff(term, xi) for xi in x]
+    resid = sp.simplify(term - sum(c * xi for c, xi in zip(tc, x)))
+    if resid != 0 or any(c.has(*x) or c.has(*u) for c in tc):
+      raise NotImplementedError(f"{name}: only terminal costs linear in x_T are generated")
+  out.append(f"  static constexpr bool has_terminal = {'true' if d['term'] is not None else 'false'};")
+  lines_tc = ["  MYR_HD static void terminal_coef(const double* p, double* tc) {", "    (void)p;"]
+  for i, k in enumerate(pn):
+    lines_tc.append(f"    const double p_{k} = p[{i}];")
+  for i in range(n):
+    lines_tc.append(f"    tc[{i}] = {cc(tc[i])};")
+  lines_tc.append("  }")
+  out += lines_tc
   out.append("};")
   out.append("")
   return out
