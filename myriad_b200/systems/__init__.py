@@ -153,6 +153,20 @@ class Tumour(FiniteHorizonControlSystem):
     return x_T[0]
 
 
+class PredatorPrey(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/predator_prey.py:47-122: only the third state has a terminal value (x_T = [None, None, B]);
+  like in the reference, both collocation transcriptions need a fully specified x_T (trapezoidal.py:70-71, hermite_simpson.py:37-48
+  raise on the None entries) -- use SHOOTING."""
+
+  def __init__(self, d_1=.1, d_2=.1, A=1., B=5., guess_a=-.52, guess_b=.5, M=1., x_0=(10., 1., 0.), T=10.):
+    super().__init__(x_0=np.array([x_0[0], x_0[1], x_0[2]], dtype=np.float64), x_T=[None, None, B], T=T,
+                     bounds=np.array([[0., 11.], [0., 11.], [0., 5.], [0., M]]), terminal_cost=True, discrete=False,
+                     device_name="PREDATORPREY", params=[d_1, d_2, A])
+
+  def terminal_cost_fn(self, x_T, u_T, T=None):
+    return x_T[0]
+
+
 class NodeSystem(FiniteHorizonControlSystem):
   """myriad/systems/neural_ode/node_system.py:14-42: a system whose (parametrized) dynamics is the neural-ODE MLP of
   myriad/neural_ode/create_node.py:110-117 applied to concat(x, u), while cost, bounds, horizon, start/end states and
@@ -238,7 +252,7 @@ class SystemType(Enum):
   GLUCOSE = Glucose
   TIMBERHARVEST = TimberHarvest
   BIOREACTOR = Bioreactor
-  PREDATORPREY = _NotOnDevice("PREDATORPREY")
+  PREDATORPREY = PredatorPrey
   INVASIVEPLANT = _NotOnDevice("INVASIVEPLANT")
   ROCKETLANDING = _NotOnDevice("ROCKETLANDING")
 

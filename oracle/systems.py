@@ -308,13 +308,32 @@ class Tumour(OracleSystem):
     pp, q, u0 = x[..., 0], x[..., 1], u[..., 0]
     return _stack([-p["xi"] * pp * xp.log(pp / q),                                             # tumour.py:79
                    q * (p["b"] - (p["mu"] + p["d"] * pp ** (2 / 3) + p["G"] * u0)),            # :80
-                   u0 + 0 * pp], x)                                                            # :81
+                   u0], x)                                                            # :81
 
   def cost(self, x, u, t):
     return 0 * x[..., 0]  # tumour.py:98
 
   def terminal_cost_fn(self, x, u):
     return x[..., 0]  # tumour.py:106-108
+
+
+class PredatorPrey(OracleSystem):
+  """myriad/systems/lenhart/predator_prey.py:47-122"""
+
+  def __init__(self, d_1=.1, d_2=.1, A=1., B=5., M=1., x_0=(10., 1., 0.), T=10.):
+    super().__init__("PREDATORPREY", np.array([x_0[0], x_0[1], x_0[2]]), [None, None, B], T,
+                     np.array([[0., 11.], [0., 11.], [0., 5.], [0., M]]), True, dict(d_1=d_1, d_2=d_2, A=A))
+
+  def dynamics(self, x, u):
+    p = self.params
+    x0, x1, u0 = x[..., 0], x[..., 1], u[..., 0]
+    return _stack([(1 - x1) * x0 - p["d_1"] * x0 * u0, (x0 - 1) * x1 - p["d_2"] * x1 * u0, u0], x)  # :86-90
+
+  def cost(self, x, u, t):
+    return self.params["A"] * 0.5 * u[..., 0] ** 2  # predator_prey.py:114
+
+  def terminal_cost_fn(self, x, u):
+    return x[..., 0]  # predator_prey.py:122
 
 
 class NodeSystem(OracleSystem):
@@ -378,6 +397,7 @@ SYSTEMS = {
   "HIVTREATMENT": HIVTreatment,
   "BACTERIA": Bacteria,
   "TUMOUR": Tumour,
+  "PREDATORPREY": PredatorPrey,
 }
 
 

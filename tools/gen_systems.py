@@ -168,6 +168,12 @@ def system_defs():
       lambda x, u, t, p: sp.Integer(0),
       term=lambda x, u, p: x[0],
       ref="myriad/systems/miscellaneous/tumour.py:77-108")
+  # myriad/systems/lenhart/predator_prey.py:47-122 (terminal cost x_0(T); x_T = [None, None, B])
+  add("PREDATORPREY", 15, 3, 1, [("d_1", 0.1), ("d_2", 0.1), ("A", 1.0)],
+      lambda x, u, p: [(1 - x[1]) * x[0] - p["d_1"] * x[0] * u[0], (x[0] - 1) * x[1] - p["d_2"] * x[1] * u[0], u[0]],
+      lambda x, u, t, p: p["A"] * sp.Rational(1, 2) * u[0] ** 2,
+      term=lambda x, u, p: x[0],
+      ref="myriad/systems/lenhart/predator_prey.py:82-122")
   return S
 
 
