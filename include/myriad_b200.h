@@ -52,6 +52,7 @@ enum {
   MYR_SYS_BACTERIA = 13,
   MYR_SYS_TUMOUR = 14,
   MYR_SYS_PREDATORPREY = 15,
+  MYR_SYS_BEARPOPULATIONS = 16,
   /* NodeSystem (myriad/systems/neural_ode/node_system.py:14-42) wrapping true system k: id = MYR_SYS_NODE_BASE + k.
    * Dynamics = the NODE MLP of myriad/neural_ode/create_node.py:110-117 (weights in MyrDesc.theta); cost, bounds,
    * horizon and the verification rollout are the true system's. */

@@ -33,6 +33,7 @@ double system_default_T(int id) {
     case MYR_SYS_BACTERIA: return 1.0;
     case MYR_SYS_TUMOUR: return 1.2;
     case MYR_SYS_PREDATORPREY: return 10.0;
+    case MYR_SYS_BEARPOPULATIONS: return 25.0;
     default: return 1.0;
   }
 }

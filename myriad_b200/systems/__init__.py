@@ -167,6 +167,15 @@ class PredatorPrey(FiniteHorizonControlSystem):
     return x_T[0]
 
 
+class BearPopulations(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/bear_populations.py:36-110 (two controls)"""
+
+  def __init__(self, r=.1, K=.75, m_p=.5, m_f=.5, c_p=10_000, c_f=10, x_0=(.4, .2, 0.), T=25):
+    super().__init__(x_0=np.array([x_0[0], x_0[1], x_0[2]], dtype=np.float64), x_T=None, T=T,
+                     bounds=np.array([[0., 2.], [0., 2.], [0., 2.], [0., .2], [0., .2]]), terminal_cost=False, discrete=False,
+                     device_name="BEARPOPULATIONS", params=[r, K, m_p, m_f, c_p, c_f])
+
+
 class NodeSystem(FiniteHorizonControlSystem):
   """myriad/systems/neural_ode/node_system.py:14-42: a system whose (parametrized) dynamics is the neural-ODE MLP of
   myriad/neural_ode/create_node.py:110-117 applied to concat(x, u), while cost, bounds, horizon, start/end states and
@@ -248,7 +257,7 @@ class SystemType(Enum):
   EPIDEMICSEIRN = EpidemicSEIRN
   HARVEST = Harvest
   HIVTREATMENT = HIVTreatment
-  BEARPOPULATIONS = _NotOnDevice("BEARPOPULATIONS")
+  BEARPOPULATIONS = BearPopulations
   GLUCOSE = Glucose
   TIMBERHARVEST = TimberHarvest
   BIOREACTOR = Bioreactor

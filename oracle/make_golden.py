@@ -71,6 +71,11 @@ CASES = {
   "x_tumour_trap_10": ("TUMOUR", "COLLOCATION", "TRAPEZOIDAL", "HEUN", 10, 1),
   "x_tumour_shooting_2x6_rk4": ("TUMOUR", "SHOOTING", "TRAPEZOIDAL", "RK4", 2, 6),
   "x_predprey_shooting_100x1_heun": ("PREDATORPREY", "SHOOTING", "TRAPEZOIDAL", "HEUN", 100, 1),
+  # two controls (the control-bound rows are filled control-major like in the reference: SURVEY 9-2)
+  "x_bear_trap_10": ("BEARPOPULATIONS", "COLLOCATION", "TRAPEZOIDAL", "HEUN", 10, 1),
+  "x_bear_hs_6": ("BEARPOPULATIONS", "COLLOCATION", "HERMITE_SIMPSON", "RK4", 6, 1),
+  "x_bear_shooting_3x4_heun": ("BEARPOPULATIONS", "SHOOTING", "TRAPEZOIDAL", "HEUN", 3, 4),
+  "x_bear_shooting_2x3_rk4": ("BEARPOPULATIONS", "SHOOTING", "TRAPEZOIDAL", "RK4", 2, 3),
   # BASELINE config C5: CARTPOLE with neural-ODE MLP dynamics (3 x 64), planned the way the reference's
   # plan_with_node_model does (myriad/utils.py:230-242: system.dynamics <- net.apply(params, append(x, u))).
   # Weights: tests/golden/node_cartpole_64x64x64.npz (tools/fit_node.py).
@@ -110,7 +115,7 @@ SOLVE_CASES = [
   "c1_simplecase_shooting_10x100_heun", "t_simplecase_shooting_1x50_heun", "t_simplecase_trap_50",
   "t_simplecase_hs_50", "s_vanderpol_trap_20", "s_cancer_trap_20", "s_cartpole_trap_10",
   "t_simplecase_shooting_20x3_heun", "s_vanderpol_hs_10", "n_node_cartpole_trap_10",
-  "x_mould_trap_10", "x_glucose_trap_10", "x_seir_trap_10", "x_hiv_trap_10", "x_bacteria_trap_10", "x_bacteria_shooting_3x5_heun", "x_tumour_trap_10", "x_predprey_shooting_100x1_heun",  "x_harvest_trap_10", "x_scwb_shooting_4x5_heun",
+  "x_mould_trap_10", "x_glucose_trap_10", "x_seir_trap_10", "x_hiv_trap_10", "x_bacteria_trap_10", "x_bacteria_shooting_3x5_heun", "x_tumour_trap_10", "x_predprey_shooting_100x1_heun", "x_bear_trap_10", "x_bear_shooting_3x4_heun",  "x_harvest_trap_10", "x_scwb_shooting_4x5_heun",
 ]
 
 

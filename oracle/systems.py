@@ -336,6 +336,29 @@ class PredatorPrey(OracleSystem):
     return x[..., 0]  # predator_prey.py:122
 
 
+class BearPopulations(OracleSystem):
+  """myriad/systems/lenhart/bear_populations.py:36-110"""
+
+  def __init__(self, r=.1, K=.75, m_p=.5, m_f=.5, c_p=10_000, c_f=10, x_0=(.4, .2, 0.), T=25):
+    super().__init__("BEARPOPULATIONS", np.array([x_0[0], x_0[1], x_0[2]]), None, T,
+                     np.array([[0., 2.], [0., 2.], [0., 2.], [0., .2], [0., .2]]), False,
+                     dict(r=r, K=K, m_p=m_p, m_f=m_f, c_p=c_p, c_f=c_f))
+
+  def dynamics(self, x, u):
+    p = self.params
+    r, K, m_p, m_f = p["r"], p["K"], p["m_p"], p["m_f"]
+    k, k2 = r / K, r / K ** 2
+    x0, x1 = x[..., 0], x[..., 1]
+    u0, u1 = u[..., 0], u[..., 1]
+    return _stack([r * x0 - k * x0 ** 2 + k * m_f * (1 - x0 / K) * x1 ** 2 - u0 * x0,                          # :78
+                   r * x1 - k * x1 ** 2 + k * m_p * (1 - x1 / K) * x0 ** 2 - u1 * x1,                          # :79
+                   k * (1 - m_p) * x0 ** 2 + k * (1 - m_f) * x1 ** 2 + k2 * m_f * x0 * x1 ** 2 + k2 * m_p * (x0 ** 2) * x1], x)  # :80-81
+
+  def cost(self, x, u, t):
+    p = self.params
+    return x[..., 2] + p["c_p"] * u[..., 0] ** 2 + p["c_f"] * u[..., 1] ** 2  # bear_populations.py:110
+
+
 class NodeSystem(OracleSystem):
   """NODE-dynamics wrapper: myriad/systems/neural_ode/node_system.py:14-42 with the MLP of
   myriad/neural_ode/create_node.py:110-117 (hk.Linear = x @ w + b, sigmoid between layers).
@@ -398,6 +421,7 @@ SYSTEMS = {
   "BACTERIA": Bacteria,
   "TUMOUR": Tumour,
   "PREDATORPREY": PredatorPrey,
+  "BEARPOPULATIONS": BearPopulations,
 }
 
 

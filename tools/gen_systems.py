@@ -174,6 +174,17 @@ def system_defs():
       lambda x, u, t, p: p["A"] * sp.Rational(1, 2) * u[0] ** 2,
       term=lambda x, u, p: x[0],
       ref="myriad/systems/lenhart/predator_prey.py:82-122")
+  # myriad/systems/lenhart/bear_populations.py:36-110 (two controls)
+  def bear_f(x, u, p):
+    k = p["r"] / p["K"]
+    k2 = p["r"] / p["K"] ** 2
+    return [p["r"] * x[0] - k * x[0] ** 2 + k * p["m_f"] * (1 - x[0] / p["K"]) * x[1] ** 2 - u[0] * x[0],
+            p["r"] * x[1] - k * x[1] ** 2 + k * p["m_p"] * (1 - x[1] / p["K"]) * x[0] ** 2 - u[1] * x[1],
+            k * (1 - p["m_p"]) * x[0] ** 2 + k * (1 - p["m_f"]) * x[1] ** 2 + k2 * p["m_f"] * x[0] * x[1] ** 2
+            + k2 * p["m_p"] * (x[0] ** 2) * x[1]]
+  add("BEARPOPULATIONS", 16, 3, 2, [("r", 0.1), ("K", 0.75), ("m_p", 0.5), ("m_f", 0.5), ("c_p", 10000.0), ("c_f", 10.0)],
+      bear_f, lambda x, u, t, p: x[2] + p["c_p"] * u[0] ** 2 + p["c_f"] * u[1] ** 2,
+      ref="myriad/systems/lenhart/bear_populations.py:71-110")
   return S
 
 
