@@ -127,7 +127,7 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one eval_kernel launch at B=8192 (ncu --set full, round 1)
-K1_NCU_TRAFFIC_BYTES = 295.45e6
+K1_NCU_TRAFFIC_BYTES = 297.45e6
 
 
 def ipm_flops_per_iteration(sz) -> dict:

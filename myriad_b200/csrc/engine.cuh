@@ -1161,7 +1161,10 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       alpha = a2;
     }
     hard_iters = ls_used >= 4 ? hard_iters + 1 : 0;
-    if (hard_iters >= 2) soc_armed = true;
+#ifndef MYR_SOC_ARM_AFTER
+#define MYR_SOC_ARM_AFTER 2
+#endif
+    if (hard_iters >= MYR_SOC_ARM_AFTER) soc_armed = true;
     if (!accepted) { status = (E0 <= O.acceptable_tol) ? ST_ACCEPTABLE : ST_LINESEARCH; break; }
 
     MYR_PH(5);
