@@ -896,9 +896,6 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
 
   MYR_PH_DECL
   double mu = O.mu_init, nu = 1.0, delta_last = 0.0;
-#ifdef MYR_COUNT_KKT
-  int n_kkt = 0;
-#endif
   int it = 0, status = ST_MAXITER, n_acceptable = 0, hard_iters = 0;
   bool soc_armed = false;
   double f = 0.0, E0 = INFINITY, cinf = INFINITY, c1 = 0.0;
@@ -995,9 +992,6 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     double delta = 0.0;
     bool ok = false;
     for (int tries = 0; tries < 60; ++tries) {
-#ifdef MYR_COUNT_KKT
-      ++n_kkt;
-#endif
       // accurate steps only matter near the solution: refine the linear solve in the end game only
       ok = kkt_solve<S>(P, L, w, sig_sh, fix_sh, delta, O.delta_c, cr, red, O.delta_reg, E0 < 1e-3 ? O.max_refine : 0);
       if (ok) break;
@@ -1200,9 +1194,6 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
   }
   InstResult res;
   res.f = f; res.E0 = E0; res.cinf = cinf; res.status = status; res.iters = it;
-#ifdef MYR_COUNT_KKT
-  res.iters = it + 10000 * n_kkt;  // experiment: number of KKT factorisations in the upper digits
-#endif
   return res;
 }
 
