@@ -21,8 +21,10 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(ROOT, "build")
 LIB = os.path.join(HERE, "libmyriad_b200.so")
 
-# true systems that also get a NodeSystem wrapper (neural-ODE dynamics on the tensor-core path, csrc/node_mlp.cuh)
-NODE_SYSTEMS = ["CARTPOLE", "VANDERPOL", "CANCERTREATMENT"]
+# true systems that also get a NodeSystem wrapper (neural-ODE dynamics on the tensor-core path, csrc/node_mlp.cuh).
+# Each wrapper is one more translation unit (~3 CPU-minutes); BASELINE config C5 needs CARTPOLE.  Others:
+#   MYR_NODE_SYSTEMS=CARTPOLE,VANDERPOL,CANCERTREATMENT python -m myriad_b200.build
+NODE_SYSTEMS = [s for s in os.environ.get("MYR_NODE_SYSTEMS", "CARTPOLE").split(",") if s]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
@@ -70,7 +72,7 @@ def build(force: bool = False, systems=None, jobs: int | None = None, verbose: b
       raise KeyError(f"system {s} has no generated device code (tools/gen_systems.py)")
   src_t = _newest_source()
   sys_src_t = _newest_source(exclude=("api.cu",))  # the per-system units do not include the dispatcher
-  tag = "_".join(sorted(names))
+  tag = "_".join(sorted(names)) + "|node:" + "_".join(sorted(s for s in NODE_SYSTEMS if s in names))
   stamp = os.path.join(BUILD, "systems.txt")
   prev = open(stamp).read() if os.path.exists(stamp) else ""
   jobs = jobs or min(8, os.cpu_count() or 1)
