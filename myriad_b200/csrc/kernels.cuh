@@ -485,7 +485,7 @@ template <class S>
 struct SmemPlan {
   size_t red, sig, fix, cr, mlp, total;
   bool cr_in_smem;
-  explicit SmemPlan(const Problem& P, size_t budget = 200 * 1024) {
+  explicit SmemPlan(const Problem& P, size_t budget = 226 * 1024) {  // 227 KB is the per-CTA maximum on sm_100
     const Layout<S> L(P);
     red = 64 * sizeof(double);
     sig = (size_t)L.Q * S::NW * sizeof(double);
