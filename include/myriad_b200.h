@@ -16,8 +16,9 @@
  *  - every function returns 0 on success or a negative MYR_E_* code; myr_last_error() gives the
  *    thread-local message.  Nothing throws across the ABI.  Work is enqueued asynchronously on
  *    the given stream; the caller synchronises.
- *  - myr_host_* are single-threaded CPU builds of the same templates taking HOST pointers.  They
- *    exist for debugging / CI without a GPU; the Python product path never calls them.
+ *  - myr_host_* are CPU builds of the same templates taking HOST pointers (OpenMP over instances).  They
+ *    exist for debugging / CI without a GPU and as bench.py's same-algorithm CPU baseline; the Python
+ *    product path never calls them.
  */
 #ifndef MYRIAD_B200_H
 #define MYRIAD_B200_H
@@ -29,10 +30,15 @@
 extern "C" {
 #endif
 
-#define MYR_ABI_VERSION 2
+#define MYR_ABI_VERSION 3
 #define MYR_MAX_PARAMS 16
 #define MYR_MAX_NODE_LAYERS 5   /* Linear layers of a NODE MLP: up to 4 hidden + the output layer */
 #define MYR_MAX_NODE_WIDTH 128  /* widest hidden layer */
+/* Workspace of myr_kkt_solve / myr_ipm_solve: a header followed by SLOTS.  A slot belongs to a resident CTA (host
+ * twin: to a thread), not to an instance, so the workspace does not grow with the batch:
+ *     ws_doubles >= MYR_WS_HEADER + min(B, MyrSizes.ipm_workspace_slots) * MyrSizes.ipm_workspace_doubles */
+#define MYR_WS_HEADER 16
+#define MYR_WS_MAX_SLOTS 2048
 
 /* SystemType members with a device implementation (myriad/systems/__init__.py:29-50). */
 enum {
@@ -112,10 +118,10 @@ typedef struct MyrSizes {
   int32_t nodes, stages;       /* node/stage structure used by the block kernels */
   int32_t nw, nc;              /* variables per node block, constraint rows per stage */
   int32_t stage_nodes;         /* node blocks per stage row in Jblk */
-  int32_t reserved;
+  int32_t ipm_workspace_slots; /* most workspace slots a call ever uses (MYR_WS_MAX_SLOTS) */
   int64_t jac_block_doubles;   /* per instance: stages * stage_nodes * nc * nw */
   int64_t hess_block_doubles;  /* per instance: nodes * nw (nw + 1) / 2 (packed upper, row-major) */
-  int64_t ipm_workspace_doubles; /* per instance */
+  int64_t ipm_workspace_doubles; /* per workspace slot (upper bound: every array in global memory) */
 } MyrSizes;
 
 /* Options of the interior-point solve; zero / negative fields take the defaults noted (IPOPT's). */
@@ -151,7 +157,7 @@ int myr_eval(const MyrDesc* desc, int B, const double* z, const double* lam,
  * by node-block elimination, Schur complement and block cyclic reduction.  sigma[i] = +inf marks an
  * eliminated (fixed) variable.  inertia_ok[b] = 1 iff the matrix has exactly ncon negative and no zero
  * eigenvalues.  Replaces the linear solver inside IPOPT (MUMPS) for this problem class.
- * ws: device workspace of at least B * ipm_workspace_doubles doubles. */
+ * ws: device workspace, see MYR_WS_HEADER. */
 int myr_kkt_solve(const MyrDesc* desc, int B, const double* Hblk, const double* Jblk, const double* sigma,
                   const double* rhs_z, const double* rhs_c, double delta_w, double delta_c,
                   double* dz, double* dlam, int32_t* inertia_ok, double* ws, size_t ws_doubles, void* stream);
@@ -178,7 +184,8 @@ int myr_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double* u, c
  * CUDA events to get the device's fp64 FMA peak, the denominator for the KKT / interior-point kernel's FLOP/s. */
 int myr_bench_dfma(int blocks, int iters, double* out, void* stream);
 
-/* Host twins (debug / CI only; HOST pointers; single-threaded). */
+/* Host twins (debug / CI and the "same algorithm on the CPU" baseline of bench.py; HOST pointers; OpenMP over
+ * instances, one workspace slot per thread). */
 int myr_host_eval(const MyrDesc* desc, int B, const double* z, const double* lam,
                   double* f, double* grad, double* c, double* Jblk, double* Hblk);
 int myr_host_kkt_solve(const MyrDesc* desc, int B, const double* Hblk, const double* Jblk, const double* sigma,

@@ -11,6 +11,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MYR_LIB", os.path.join(HERE, "libmyriad_b200.so"))  # MYR_LIB: A/B builds of the same ABI
 
+ABI_VERSION = 3
+WS_HEADER = 16  # MYR_WS_HEADER
 MAX_PARAMS = 16
 MAX_NODE_LAYERS = 5
 NODE_BASE = 100
@@ -38,7 +40,7 @@ class MyrDesc(C.Structure):
 class MyrSizes(C.Structure):
   _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("nx_nodes", C.c_int32), ("nu_nodes", C.c_int32),
               ("nvars", C.c_int32), ("ncon", C.c_int32), ("nodes", C.c_int32), ("stages", C.c_int32),
-              ("nw", C.c_int32), ("nc", C.c_int32), ("stage_nodes", C.c_int32), ("reserved", C.c_int32),
+              ("nw", C.c_int32), ("nc", C.c_int32), ("stage_nodes", C.c_int32), ("ipm_workspace_slots", C.c_int32),
               ("jac_block_doubles", C.c_int64), ("hess_block_doubles", C.c_int64),
               ("ipm_workspace_doubles", C.c_int64)]
 
@@ -130,6 +132,11 @@ def make_desc(system: str, optimizer: int, method: str, intervals: int, cpi: int
     for i, v in enumerate(params):
       d.params[i] = float(v)
   return d
+
+
+def workspace_doubles(sizes: MyrSizes, B: int) -> int:
+  """include/myriad_b200.h, MYR_WS_HEADER: a header plus one slot per resident CTA (never more than B)"""
+  return WS_HEADER + max(1, min(int(B), int(sizes.ipm_workspace_slots))) * int(sizes.ipm_workspace_doubles)
 
 
 def problem_sizes(desc: MyrDesc) -> MyrSizes:

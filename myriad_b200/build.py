@@ -27,7 +27,7 @@ LIB = os.path.join(HERE, "libmyriad_b200.so")
 NODE_SYSTEMS = [s for s in os.environ.get("MYR_NODE_SYSTEMS", "CARTPOLE").split(",") if s]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC,-fopenmp"]
 
 
 def _nvcc() -> str:
@@ -104,7 +104,7 @@ def build(force: bool = False, systems=None, jobs: int | None = None, verbose: b
         if verbose and out.strip():
           print(out)
   if tasks or not os.path.exists(LIB) or prev != tag:
-    _run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    _run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp", "-lgomp"])
     open(stamp, "w").write(tag)
     if verbose:
       print(f"[myriad_b200.build] linked {LIB}", flush=True)

@@ -1,7 +1,18 @@
 // Per-instance engine: K1 (evaluation of the transcribed NLP with block Jacobian / Hessian),
 // K2 (block-structured KKT solve: node-block inverses, Schur complement, block cyclic reduction with
-// inertia) and K3 (primal-dual interior-point iteration).  One CTA works on one problem instance;
-// threads stride over nodes / stages.  Written once for device and host (see common.cuh).
+// inertia) and K3 (primal-dual interior-point iteration).  One CTA works on one problem instance at a
+// time (persistent CTAs pull instances from a counter); threads stride over nodes / stages.  Written
+// once for device and host (see common.cuh).
+//
+// Memory plan (round 2).  All per-instance state lives in a WORKSPACE SLOT owned by the resident CTA -- not by
+// the instance -- so that the footprint is (resident CTAs) x (slot) whatever the batch.  A slot is a set of named
+// arrays; each array is placed either in the CTA's shared memory or in the slot's global-memory part (L2 resident)
+// by a priority list filled greedily against the shared-memory budget (Layout::place): the block-cyclic-reduction
+// scratch first, then the node-block inverses and the Jacobian blocks, then the iterate vectors.
+//   * matrices are "array of blocks": block q at base + q * stride, stride padded to 2 (mod 4) doubles so that
+//     consecutive nodes' 16-byte accesses fall into distinct banks and every element has a compile-time offset;
+//   * node vectors are element-major (base + i * ldq + q): coalesced in global memory, conflict-free in shared;
+//   * stage vectors are stage-major (base + j * NC + r), the layout the cyclic reduction reads.
 #pragma once
 #include <type_traits>
 
@@ -44,79 +55,130 @@ struct scheme_is_lifted<S, typename std::enable_if<S::kLifted>::type> { static c
 #define MYR_PH(idx) do { } while (0)
 #endif
 
-// ------------------------------------------------------------------ workspace layout (doubles / instance)
+// ------------------------------------------------------------------ workspace arrays
+// smallest v >= n with v = 2 (mod 4): block strides (see the header comment)
+MYR_HDI constexpr int pad2(int n) { return ((n + 1) & ~3) + 2; }
+
+template <class S>
+struct Dims {
+  static constexpr int NW = S::NW, NC = S::NC, NWP = S::NWP;
+  static constexpr int GS = pad2(NC * NW);   // Jacobian block of a node role
+  static constexpr int HS = pad2(NW * NW);   // node-block inverse (full)
+  static constexpr int WSZ = pad2(NWP);      // packed Hessian block
+  static constexpr int BS = pad2(NC * NC);   // Schur-complement block
+};
+
+// X(name, doubles): in shared-memory PRIORITY order
+#define MYR_WS_ARRAYS(X)                                                                                              \
+  X(crD, St * D::BS) X(crU, St * D::BS) X(crVL, St * D::BS) X(crVU, St * D::BS) X(crb, St * NC) X(dlam, St * NC)       \
+  X(Hinv, Q * D::HS) X(G, Q * D::GS) X(F, Q * D::GS)                                                                  \
+  X(lam, St * NC) X(z, ldq * NW) X(rb, ldq * NW) X(dz, ldq * NW) X(tv, ldq * NW) X(fixm, (Q + 1) / 2)                   \
+  X(W, Q * D::WSZ) X(gl, ldq * NW) X(zL, ldq * NW) X(zU, ldq * NW) X(lbr, ldq * NW) X(ubr, ldq * NW)                    \
+  X(sig, ldq * NW) X(rsl, ldq * NW) X(rsu, ldq * NW) X(dzL, ldq * NW) X(dzU, ldq * NW) X(zt, ldq * NW)                  \
+  X(phi, Q * NC) X(psi, Q * NC) X(c, St * NC) X(sch, St * NC) X(ct, St * NC)                                          \
+  X(dz2, ldq * NW) X(csoc, St * NC) X(dl2, St * NC)                                                                   \
+  X(dynf, kCoopMlp ? Q * S::n : 0) X(dynJ, kCoopMlp ? Q * S::n * NW : 0) X(dynH, kCoopMlp ? Q * S::NWP : 0)           \
+  X(ext, scheme_is_lifted<S>::value ? 6 * Q * NW + St * NC : 0)
+
 template <class S>
 struct Layout {
+  using D = Dims<S>;
+  static constexpr int NW = S::NW, NC = S::NC;
   // collocation on a NODE system: the MLP is evaluated for all nodes of the instance cooperatively (node_mlp.cuh)
   static constexpr bool kCoopMlp = sys_is_node<typename S::System>::value && !scheme_is_lifted<S>::value;
-  int Q, St;
-  int ldq, lds;   // leading dimensions of the element-major node / stage arrays
-  int G, F, W, Hinv, gl, phi, psi, rb, dz, dzL, dzU, c, dlam;
-  int crD, crU, crVL, crVU, crb, crx;
-  int lbr, ubr, rsl, rsu, zt, dz2, sch, ct, csoc, dl2;
-  int dynf, dynJ, dynH;   // NODE systems: per-node MLP dynamics values / Jacobians / contracted Hessians
-  int ext;
-  int total;
+  enum : int {
+#define X(name, sz) A_##name,
+    MYR_WS_ARRAYS(X)
+#undef X
+    A_COUNT
+  };
+  static constexpr int kCrArrays = 6;  // the leading arrays that make up the cyclic-reduction scratch
+  int Q, St, ldq;
+  int size[A_COUNT];
   MYR_HDI explicit Layout(const Problem& P) {
     Q = S::num_nodes(P); St = S::num_stages(P);
     ldq = (Q + 3) & ~3;
-    lds = ((St + 3) & ~3) + 1;  // = 1 mod 4: the NC rows of a block (stride NC * lds doubles) fall into distinct shared-memory banks
-    int o = 0;
-    G = o; o += ldq * S::NC * S::NW;
-    F = o; o += ldq * S::NC * S::NW;
-    W = o; o += ldq * S::NWP;
-    Hinv = o; o += ldq * S::NW * S::NW;
-    gl = o; o += ldq * S::NW;
-    phi = o; o += ldq * S::NC;
-    psi = o; o += ldq * S::NC;
-    rb = o; o += ldq * S::NW;
-    dz = o; o += ldq * S::NW;
-    dzL = o; o += ldq * S::NW;
-    dzU = o; o += ldq * S::NW;
-    c = o; o += lds * S::NC;
-    dlam = o; o += lds * S::NC;
-    crD = o; o += lds * S::NC * S::NC;
-    crU = o; o += lds * S::NC * S::NC;
-    crVL = o; o += lds * S::NC * S::NC;
-    crVU = o; o += lds * S::NC * S::NC;
-    crb = o; o += lds * S::NC;
-    crx = dlam;  // CR writes its solution straight into dlam
-    lbr = o; o += ldq * S::NW;   // relaxed bounds per variable (-inf / +inf: none)
-    ubr = o; o += ldq * S::NW;
-    zt = o; o += ldq * S::NW;    // trial point of the line search (reference layout, nv <= Q * NW)
-    dz2 = o; o += ldq * S::NW;   // second-order-correction step
-    sch = o; o += lds * S::NC;   // -J Hinv rb per stage (kept from the last KKT solve for re-solves)
-    ct = o; o += lds * S::NC;    // constraints at the trial point
-    csoc = o; o += lds * S::NC;  // accumulated SOC right-hand side
-    dl2 = o; o += lds * S::NC;   // multiplier step of the SOC solve
-    rsl = o; o += ldq * S::NW;   // reciprocal slacks 1 / (x - lbr), 1 / (ubr - x) of the current iterate
-    rsu = o; o += ldq * S::NW;
-    dynf = dynJ = dynH = o;
-    if (kCoopMlp) {
-      dynf = o; o += Q * S::n;
-      dynJ = o; o += Q * S::n * S::NW;
-      dynH = o; o += Q * S::NWP;
-    }
-    // lifted schemes keep their internal iterate / bounds / multipliers in the workspace too
-    ext = o;
-    if (scheme_is_lifted<S>::value) o += 6 * Q * S::NW + St * S::NC;
-    total = (o + 15) & ~15;
+#define X(name, sz) size[A_##name] = ((sz) + 1) & ~1;
+    MYR_WS_ARRAYS(X)
+#undef X
   }
-  // doubles of the CR scratch (D,U,VL,VU,b), contiguous from crD
-  MYR_HDI int cr_doubles() const { return lds * (4 * S::NC * S::NC + S::NC); }
+  // greedy placement against a shared-memory budget (doubles): bit a of the result <=> array a is in shared memory
+  MYR_HDI unsigned long long place(long long budget, int& smem_doubles, int& glob_doubles) const {
+    unsigned long long mask = 0;
+    long long used = 0, glob = 0;
+    for (int a = 0; a < A_COUNT; ++a) {
+      if (size[a] > 0 && used + size[a] <= budget) { mask |= 1ull << a; used += size[a]; }
+      else glob += size[a];
+    }
+    smem_doubles = (int)used;
+    glob_doubles = (int)((glob + 15) & ~15ll);
+    return mask;
+  }
+  MYR_HDI int cr_doubles() const { int s = 0; for (int a = 0; a < kCrArrays; ++a) s += size[a]; return s; }
 };
 
-// Workspace arrays are element-major ("structure of arrays"): element e of node q lives at  base + e * ldq + q  (stage
-// arrays: base + e * lds + j), so the threads of a warp -- one node / stage each -- touch consecutive addresses.
-#define NQ(arr, q, e) w[L.arr + (e) * L.ldq + (q)]
-#define NS(arr, j, e) w[L.arr + (e) * L.lds + (j)]
-template <class T>
-struct Strided {
-  T* p; int s;
-  MYR_HDI T& operator[](int i) const { return p[(long long)i * s]; }
+// pointers to the arrays of the slot this CTA works in
+template <class S>
+struct WS {
+  using L = Layout<S>;
+  int Q, St, ldq;
+#define X(name, sz) double* name;
+  MYR_WS_ARRAYS(X)
+#undef X
+  double* red;       // reduction scratch: 2 * kRedStride doubles
+  double* mlp_scr;   // NODE systems: scratch of the cooperative MLP pass (shared memory), else null
+  MYR_HDI WS(const L& lay, unsigned long long mask, double* smem, double* glob) {
+    Q = lay.Q; St = lay.St; ldq = lay.ldq;
+    double* sp = smem; double* gp = glob;
+#define X(name, sz) if ((mask >> L::A_##name) & 1ull) { name = sp; sp += lay.size[L::A_##name]; } else { name = gp; gp += lay.size[L::A_##name]; }
+    MYR_WS_ARRAYS(X)
+#undef X
+    red = nullptr; mlp_scr = nullptr;
+  }
+  MYR_HDI uint32_t* fix() const { return reinterpret_cast<uint32_t*>(fixm); }
 };
-using SV = Strided<double>;
-using CSV = Strided<const double>;
+
+#define NQ(arr, q, e) ws.arr[(e) * ws.ldq + (q)]
+#define NS(arr, j, r) ws.arr[(j) * NC + (r)]
+
+// ------------------------------------------------------------------ fused block reductions
+// K values are reduced in ONE pass (independent shuffle chains, one barrier): a per-quantity block_sum costs two
+// barriers and a dependent shuffle chain each, and the interior-point iteration needs about twenty of them.
+// red: 2 * kRedStride doubles of shared memory, used alternately (parity) so that no leading barrier is needed.
+constexpr int kRedMaxK = 12;
+constexpr int kRedStride = 8 * kRedMaxK;
+enum RedOp : int { R_SUM = 0, R_MAX = 1, R_MIN = 2 };
+MYR_HDI double red_apply(int op, double a, double b) { return op == R_SUM ? a + b : (op == R_MAX ? fmax(a, b) : fmin(a, b)); }
+
+template <int... OPS>
+MYR_HDI void block_reduce_multi(double* v, double* red, int& parity) {
+#ifdef __CUDA_ARCH__
+  constexpr int K = sizeof...(OPS);
+  static_assert(K <= kRedMaxK, "too many fused reductions");
+  constexpr int ops[K] = {OPS...};
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = red_apply(ops[k], v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+  }
+  double* buf = red + parity * kRedStride;
+  parity ^= 1;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) buf[w * K + k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double r = buf[k];
+    for (int ww = 1; ww < nw; ++ww) r = red_apply(ops[k], r, buf[ww * K + k]);
+    v[k] = r;
+  }
+#else
+  (void)v; (void)red; (void)parity;
+#endif
+}
 
 // ------------------------------------------------------------------ bounds helpers
 struct Bnd {
@@ -146,104 +208,116 @@ struct LogProd {
   MYR_HDI double value() const { return bad ? NAN : sum + log(prod); }
 };
 
+// multipliers of the slot's lam array as the schemes' node_mu wants them
+template <int NC>
+struct WsLamView {
+  const double* lam;
+  MYR_HDI double operator()(int j, int r) const { return lam[j * NC + r]; }
+};
+// iterate of the slot (element-major)
+struct WsZView {
+  const double* z; int ldq;
+  MYR_HDI double operator()(int q, int i) const { return z[i * ldq + q]; }
+};
+
 // ------------------------------------------------------------------ K1: node evaluation sweep
-// Evaluates every node at point z (reference layout), stores node arrays in the workspace and returns the
-// objective.  MODE as in schemes.cuh.  zsrc may be the iterate or a trial point.
+// Evaluates every node at the point zv (element-major node vector: the iterate or a trial point) and stores the node
+// arrays in the slot.  MODE as in schemes.cuh; MODE 2 also leaves  grad f + J^T lam  (zero on fixed variables) in rb.
+// Returns this thread's part of the objective (the caller reduces it together with its other sums).
 template <class S, int MODE>
-MYR_HDI double eval_nodes(const Problem& P, const Layout<S>& L, const double* z, const double* lam, double* w, double* red,
-                          double* mlp_scr = nullptr) {
-  const int Q = L.Q;
+MYR_HDI double eval_nodes(const Problem& P, const WS<S>& ws, const double* zv) {
+  using D = Dims<S>;
+  constexpr int NW = S::NW, NC = S::NC;
+  const int Q = ws.Q;
   double fsum = 0.0;
   bool have_pre = false;
 #ifdef __CUDA_ARCH__
   if constexpr (Layout<S>::kCoopMlp) {
-    mlp_nodes_pass<S, MODE>(P, Q, z, lam, w + L.dynf, w + L.dynJ, w + L.dynH, mlp_scr);
+    mlp_nodes_pass<S, MODE>(P, Q, WsZView{zv, ws.ldq}, WsLamView<NC>{ws.lam}, ws.dynf, ws.dynJ, ws.dynH, ws.mlp_scr);
     have_pre = true;
   }
 #endif
   for (int q = MYR_TID; q < Q; q += MYR_NT) {
     PreDyn pre;
-    if (have_pre) { pre.f = w + L.dynf + q * S::n; pre.J = w + L.dynJ + q * S::n * S::NW; pre.H = w + L.dynH + q * S::NWP; }
-    double v[S::NW], lp[S::NC], ls[S::NC];
+    if (have_pre) { pre.f = ws.dynf + q * S::n; pre.J = ws.dynJ + q * S::n * NW; pre.H = ws.dynH + q * S::NWP; }
+    double v[NW], lp[NC], ls[NC];
 #pragma unroll
-    for (int i = 0; i < S::NW; ++i) v[i] = z[S::zidx(P, q, i)];
+    for (int i = 0; i < NW; ++i) v[i] = zv[i * ws.ldq + q];
     const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
     if (MODE == 2) {
 #pragma unroll
-      for (int r = 0; r < S::NC; ++r) {
-        lp[r] = jp >= 0 ? lam[S::cidx(P, jp, r)] : 0.0;
-        ls[r] = js >= 0 ? lam[S::cidx(P, js, r)] : 0.0;
+      for (int r = 0; r < NC; ++r) {
+        lp[r] = jp >= 0 ? NS(lam, jp, r) : 0.0;
+        ls[r] = js >= 0 ? NS(lam, js, r) : 0.0;
       }
     }
-    double ell, gl[S::NW], phi[S::NC], psi[S::NC], G[S::NC * S::NW], F[S::NC * S::NW], W[S::NWP];
+    double ell, gl[NW], phi[NC], psi[NC], G[NC * NW], F[NC * NW], W[S::NWP];
     S::template eval_node<MODE>(P, q, v, lp, ls, ell, gl, phi, psi, G, F, W, pre);
     fsum += ell;
 #pragma unroll
-    for (int r = 0; r < S::NC; ++r) { NQ(phi, q, r) = phi[r]; NQ(psi, q, r) = psi[r]; }
+    for (int r = 0; r < NC; ++r) { ws.phi[q * NC + r] = phi[r]; ws.psi[q * NC + r] = psi[r]; }
     if (MODE >= 1) {
 #pragma unroll
-      for (int i = 0; i < S::NW; ++i) NQ(gl, q, i) = gl[i];
+      for (int i = 0; i < NW; ++i) NQ(gl, q, i) = gl[i];
+      double* Gq = ws.G + q * D::GS; double* Fq = ws.F + q * D::GS;
 #pragma unroll
-      for (int i = 0; i < S::NC * S::NW; ++i) { NQ(G, q, i) = G[i]; NQ(F, q, i) = F[i]; }
+      for (int i = 0; i < NC * NW; ++i) { Gq[i] = G[i]; Fq[i] = F[i]; }
     }
     if (MODE == 2) {
+      double* Wq = ws.W + q * D::WSZ;
 #pragma unroll
-      for (int i = 0; i < S::NWP; ++i) NQ(W, q, i) = W[i];
+      for (int i = 0; i < S::NWP; ++i) Wq[i] = W[i];
+      const uint32_t fm = ws.fix()[q];
+#pragma unroll
+      for (int i = 0; i < NW; ++i) {
+        double r = gl[i];
+#pragma unroll
+        for (int rr = 0; rr < NC; ++rr) r += G[rr * NW + i] * lp[rr] + F[rr * NW + i] * ls[rr];
+        NQ(rb, q, i) = ((fm >> i) & 1u) ? 0.0 : r;
+      }
     }
   }
-  const double f = block_sum(fsum, red);
-  MYR_SYNC();
-  return f;
+  return fsum;
 }
 
-// stage constraints from node role values; writes c (stage-major) and returns (inf-norm, 1-norm)
+// stage constraints from node role values; writes cdst (stage-major) and accumulates this thread's (max |c|, sum |c|)
 template <class S>
-MYR_HDI void stage_constraints(const Problem& P, const Layout<S>& L, double* w, double* cdst, double* red, double& cinf, double& c1) {
-  double mx = 0.0, sm = 0.0;
-  for (int j = MYR_TID; j < L.St; j += MYR_NT) {
+MYR_HDI void stage_constraints(const Problem& P, const WS<S>& ws, double* cdst, double& mx, double& sm) {
+  constexpr int NC = S::NC;
+  for (int j = MYR_TID; j < ws.St; j += MYR_NT) {
     const int nk = S::stage_nodes(P, j);
+    double a[NC];
 #pragma unroll
-    for (int r = 0; r < S::NC; ++r) {
-      double a = 0.0;
-      for (int k = 0; k < nk; ++k) {
-        int role; const int q = S::stage_node(P, j, k, role);
-        a += role ? NQ(psi, q, r) : NQ(phi, q, r);
-      }
-      cdst[r * L.lds + j] = a;
-      const double aa = (a != a) ? INFINITY : fabs(a);
+    for (int r = 0; r < NC; ++r) a[r] = 0.0;
+    for (int k = 0; k < nk; ++k) {
+      int role; const int q = S::stage_node(P, j, k, role);
+      const double* src = (role ? ws.psi : ws.phi) + q * NC;
+#pragma unroll
+      for (int r = 0; r < NC; ++r) a[r] += src[r];
+    }
+#pragma unroll
+    for (int r = 0; r < NC; ++r) {
+      cdst[j * NC + r] = a[r];
+      const double aa = (a[r] != a[r]) ? INFINITY : fabs(a[r]);
       mx = fmax(mx, aa); sm += aa;
     }
   }
-  cinf = block_max(mx, red);
-  c1 = block_sum(sm, red);
-  MYR_SYNC();
 }
 
 // ------------------------------------------------------------------ K2 pieces
-// small dense helpers on row-major blocks
-template <int R, int K, int C, class TA, class TB>
-MYR_HDI void mm(const TA& A, const TB& Bm, double* Cm) {  // C = A(RxK) B(KxC)
-#pragma unroll
-  for (int i = 0; i < R; ++i)
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < K; ++k) s += A[i * K + k] * Bm[k * C + j];
-      Cm[i * C + j] = s;
-    }
-}
 // Block cyclic reduction for the symmetric block-tridiagonal system
 //   U_{i-1}^T x_{i-1} + D_i x_i + U_i x_{i+1} = b_i,   i = 0..St-1,  blocks NC x NC (D symmetric, may be indefinite).
 // Factor and solve are fused (single right-hand side).  Pivot-block inertias are accumulated: by Sylvester's
 // law their sum is the inertia of the whole matrix.  D,U,b are destroyed; x receives the solution.
-// All block arrays are element-major with leading dimension ld: entry k of block i is at  A[k * ld + i].
+// Blocks are stored one after the other with stride BS = pad2(NC*NC) (row-major inside); b and x are stage-major.
 //
-// Work decomposition: a GROUP of G = pow2 >= NC adjacent lanes owns one block; lane r of the group produces ROW r of
-// every block product of that block (the pivot-block inverse is computed redundantly by the lanes of the group: it is
-// a serial chain anyway).  With one thread per block the cost of a level does not shrink with the number of blocks
-// left, and the deep levels (13, 6, 3, 2, 1 blocks) dominate; with row-parallel groups a level costs roughly the
-// latency of one inverse plus a few row products.  On the host (one "thread") a group degenerates to a loop over rows.
+// Work decomposition: a GROUP of G = pow2 >= NC adjacent lanes owns one block; lane r of the group holds / produces
+// ROW r.  The pivot-block inverse is computed COOPERATIVELY by the group (Gauss-Jordan without pivoting, the pivot row
+// broadcast with warp shuffles; the pivots are those of the LDL^T factorisation, so their signs give the inertia and
+// the same acceptance test applies), which needs NC registers per lane instead of NC^2 -- that is what lets the
+// 8 x 8 blocks of Hermite-Simpson run without spills.  A block whose natural-order pivots are not acceptable (very rare)
+// falls back to the pivoted Bunch-Parlett routine, executed redundantly by the lanes of the group.
+// On the host (one "thread") a group degenerates to a loop over rows around a full Gauss-Jordan inverse.
 template <int NC>
 struct CrGroup { static constexpr int G = NC <= 1 ? 1 : (NC <= 2 ? 2 : (NC <= 4 ? 4 : (NC <= 8 ? 8 : 16))); };
 
@@ -253,80 +327,188 @@ struct CrGroup { static constexpr int G = NC <= 1 ? 1 : (NC <= 2 ? 2 : (NC <= 4 
 #define MYR_CR_ROWS(r) for (int r = 0; r < NC; ++r)
 #endif
 
+// host: full Gauss-Jordan inverse without pivoting, same arithmetic as the cooperative device version
+template <int N>
+inline bool gj_inverse_full(double* a /* N x N in/out */, int& np, int& nn) {
+  double sc = 0.0;
+  for (int i = 0; i < N * N; ++i) sc = fmax(sc, fabs(a[i]));
+  const double tiny = 1e-14 * sc;
+  bool ok = true;
+  np = nn = 0;
+  for (int k = 0; k < N; ++k) {
+    double rk[N];
+    for (int j = 0; j < N; ++j) rk[j] = a[k * N + j];
+    const double p = rk[k];
+    double colmax = 0.0;
+    for (int j = k + 1; j < N; ++j) colmax = fmax(colmax, fabs(rk[j]));
+    ok = ok && (fabs(p) > 1e-7 * colmax) && (fabs(p) > tiny);
+    if (p > 0) ++np; else ++nn;
+    const double ip = 1.0 / p;
+    for (int r = 0; r < N; ++r) {
+      const double f = a[r * N + k];
+      for (int j = 0; j < N; ++j) {
+        if (j == k) continue;
+        const double s = rk[j] * ip;
+        a[r * N + j] = (r == k) ? s : a[r * N + j] - f * s;
+      }
+      a[r * N + k] = (r == k) ? ip : -f * ip;
+    }
+  }
+  return ok;
+}
+
+#ifdef __CUDA_ARCH__
+// device: lane r of a G-lane group holds row r of the block in a[]; on return a[] is row r of the inverse.
+// Must be executed by all 32 lanes of the warp.  ok / np / nn are identical on all lanes of a group.
+template <int N, int G>
+__device__ __forceinline__ void coop_inverse(double (&a)[N], int r, bool& ok, int& np, int& nn) {
+  double sc = 0.0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) sc = fmax(sc, fabs(a[j]));
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) sc = fmax(sc, __shfl_xor_sync(0xffffffffu, sc, o));
+  const double tiny = 1e-14 * sc;
+  ok = true; np = 0; nn = 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double rk[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) rk[j] = __shfl_sync(0xffffffffu, a[j], k, G);
+    const double p = rk[k];
+    double colmax = 0.0;
+#pragma unroll
+    for (int j = k + 1; j < N; ++j) colmax = fmax(colmax, fabs(rk[j]));
+    ok = ok && (fabs(p) > 1e-7 * colmax) && (fabs(p) > tiny);
+    if (p > 0) ++np; else ++nn;
+    const double ip = 1.0 / p;
+    const double f = a[k];
+    const bool piv = (r == k);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      if (j == k) continue;
+      const double s = rk[j] * ip;
+      a[j] = piv ? s : a[j] - f * s;
+    }
+    a[k] = piv ? ip : -f * ip;
+  }
+}
+#endif
+
 template <int NC>
-MYR_HDI void block_cr_solve(int St, int ld, double* D, double* U, double* VL, double* VU, double* b, double* x,
-                            double* red, int& npos, int& nneg, int& nzero) {
+MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU, double* b, double* x,
+                            int& cp, int& cn, int& cz) {
   constexpr int BB = NC * NC;
+  constexpr int BS = pad2(BB);
   constexpr int G = CrGroup<NC>::G;
 #ifdef __CUDA_ARCH__
   const int grp = int(threadIdx.x) / G, ngrp = int(blockDim.x) / G;
-  const bool counter = (int(threadIdx.x) % G) == 0;
+  const int rl = int(threadIdx.x) % G;
+  const bool rvalid = rl < NC;
+  const bool counter = rl == 0;
 #else
   const int grp = 0, ngrp = 1;
   const bool counter = true;
 #endif
-  int cp = 0, cn = 0, cz = 0;
+  cp = cn = cz = 0;
 #if defined(MYR_PROFILE_PHASES) && defined(__CUDA_ARCH__)
   long long cph_t0_ = clock64();
 #define MYR_CPH(idx) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase_cycles[idx], (unsigned long long)(t_ - cph_t0_)); cph_t0_ = t_; } } while (0)
 #else
 #define MYR_CPH(idx) do { } while (0)
 #endif
-  // pivot inverse of block i (symmetrised on load), row r selected into dr without dynamic register indexing
-  auto pivot_rows = [&](int i, double* Dinv) {
-    double A[BB];
+  // ---- pivot-block inverse of block i.  Device: a[] = row rl of the inverse.  Host: Dinv = full inverse.
+#ifdef __CUDA_ARCH__
+  auto pivot_row = [&](int i, bool active, double (&a)[NC]) {
+    const double* Di = D + i * BS;
 #pragma unroll
-    for (int r = 0; r < NC; ++r)
+    for (int c = 0; c < NC; ++c) a[c] = rvalid ? Di[rl * NC + c] : (c == 0 ? 1.0 : 0.0);
+    bool ok; int p_, n_;
+    coop_inverse<NC, G>(a, rl, ok, p_, n_);
+    int z_ = 0;
+    if (!__all_sync(0xffffffffu, ok)) {   // rare: natural-order pivots rejected somewhere in this warp
+      if (!ok) {
+        double A[BB], inv[BB];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) A[r * NC + c] = 0.5 * (D[(r * NC + c) * ld + i] + D[(c * NC + r) * ld + i]);
-    int p_, n_, z_;
-    sym_inverse<NC>(A, 0u, Dinv, p_, n_, z_);
-    if (counter) { cp += p_; cn += n_; cz += z_; }
+        for (int r = 0; r < NC; ++r)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) A[r * NC + c] = 0.5 * (Di[r * NC + c] + Di[c * NC + r]);
+        sym_inverse_inertia<NC>(A, 0u, inv, p_, n_, z_);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          double v = 0.0;
+#pragma unroll
+          for (int rr = 0; rr < NC; ++rr) v = (rr == rl) ? inv[rr * NC + c] : v;
+          a[c] = v;
+        }
+      }
+      __syncwarp();   // every lane of the group has read D_i before rows of it are overwritten
+    }
+    if (counter && active) { cp += p_; cn += n_; cz += z_; }
   };
+#else
+  auto pivot_full = [&](int i, double* Dinv) {
+    const double* Di = D + i * BS;
+    for (int e = 0; e < BB; ++e) Dinv[e] = Di[e];
+    int p_, n_, z_ = 0;
+    if (!gj_inverse_full<NC>(Dinv, p_, n_)) {
+      double A[BB];
+      for (int r = 0; r < NC; ++r)
+        for (int c = 0; c < NC; ++c) A[r * NC + c] = 0.5 * (Di[r * NC + c] + Di[c * NC + r]);
+      sym_inverse_inertia<NC>(A, 0u, Dinv, p_, n_, z_);
+    }
+    cp += p_; cn += n_; cz += z_;
+  };
+#endif
   int s = 1;
   for (; s < St; s <<= 1) {
     const int nodd = (St - s + 2 * s - 1) / (2 * s);   // blocks i = (2k+1) s < St
     const int neven = (St + 2 * s - 1) / (2 * s);      // blocks i = 2k s < St
     // ---- eliminate the odd blocks: Dinv_i (kept in D), VL_i = Dinv_i U_{i-s}^T, VU_i = Dinv_i U_i, x_i = Dinv_i b_i
-    for (int k0 = 0; k0 < nodd; k0 += ngrp) {   // trip count uniform across the CTA (the loop contains a warp barrier)
+    for (int k0 = 0; k0 < nodd; k0 += ngrp) {   // trip count uniform across the CTA (the body contains warp shuffles)
       const int k = k0 + grp;
       const bool active = k < nodd;
       const int i = active ? (2 * k + 1) * s : s;
-      double Dinv[BB], Ul[BB], Ui[BB], bi[NC];
       const bool hr = i + s < St;
-      if (active) {
-        pivot_rows(i, Dinv);
-#pragma unroll
-        for (int e = 0; e < BB; ++e) { Ul[e] = U[e * ld + (i - s)]; Ui[e] = hr ? U[e * ld + i] : 0.0; }
-#pragma unroll
-        for (int m = 0; m < NC; ++m) bi[m] = b[m * ld + i];
-      }
 #ifdef __CUDA_ARCH__
-      __syncwarp();  // every lane of the group has read D_i before rows of it are overwritten
+      double dr[NC];
+      pivot_row(i, active, dr);
+      if (active && rvalid) {
+        const int r = rl;
+#else
+      double Dinv[BB];
+      pivot_full(i, Dinv);
+      for (int r = 0; r < NC; ++r) {
+        double dr[NC];
+        for (int m = 0; m < NC; ++m) dr[m] = Dinv[r * NC + m];
 #endif
-      if (active) {
-        MYR_CR_ROWS(r) {
-          double dr[NC];
+        const double* Ul = U + (i - s) * BS;
+        const double* Ui = U + i * BS;
+        double* Dd = D + i * BS + r * NC;
+        double* VLd = VL + i * BS + r * NC;
+        double* VUd = VU + i * BS + r * NC;
+        double xr = 0.0;
 #pragma unroll
-          for (int m = 0; m < NC; ++m) {
-            double v = 0.0;
+        for (int c = 0; c < NC; ++c) {
+          double vl = 0.0;
 #pragma unroll
-            for (int rr = 0; rr < NC; ++rr) v = (rr == r) ? Dinv[rr * NC + m] : v;
-            dr[m] = v;
-          }
-          double xr = 0.0;
-#pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            double vl = 0.0, vu = 0.0;
-#pragma unroll
-            for (int m = 0; m < NC; ++m) { vl += dr[m] * Ul[c * NC + m]; vu += dr[m] * Ui[m * NC + c]; }
-            VL[(r * NC + c) * ld + i] = vl;
-            if (hr) VU[(r * NC + c) * ld + i] = vu;
-            D[(r * NC + c) * ld + i] = dr[c];
-            xr += dr[c] * bi[c];
-          }
-          x[r * ld + i] = xr;
+          for (int m = 0; m < NC; ++m) vl += dr[m] * Ul[c * NC + m];
+          VLd[c] = vl;
+          xr += dr[c] * b[i * NC + c];
         }
+        if (hr) {
+          double vu[NC];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) vu[c] = 0.0;
+#pragma unroll
+          for (int m = 0; m < NC; ++m)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) vu[c] += dr[m] * Ui[m * NC + c];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) VUd[c] = vu[c];
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) Dd[c] = dr[c];
+        x[i * NC + r] = xr;
       }
     }
     MYR_SYNC();
@@ -336,69 +518,68 @@ MYR_HDI void block_cr_solve(int St, int ld, double* D, double* U, double* VL, do
       const int i = 2 * k * s, er = i + s, el = i - s;
       const bool hr = er < St, hl = el >= 0, hrr = hr && er + s < St;
       MYR_CR_ROWS(r) {
-        double dn[NC], un[NC], ur[NC], uc[NC];
-        double bn = b[r * ld + i];
+        double dn[NC], un[NC];
+        double* Dd = D + i * BS + r * NC;
+        double* Ud = U + i * BS + r * NC;
+        double bn = b[i * NC + r];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          dn[c] = D[(r * NC + c) * ld + i]; un[c] = 0.0;
-          ur[c] = hr ? U[(r * NC + c) * ld + i] : 0.0;      // row r of U_i
-          uc[c] = hl ? U[(c * NC + r) * ld + el] : 0.0;     // column r of U_el = row r of U_el^T
-        }
+        for (int c = 0; c < NC; ++c) { dn[c] = Dd[c]; un[c] = 0.0; }
         if (hr) {
+          const double* VLe = VL + er * BS;
+          const double* VUe = VU + er * BS;
+          const double* xe = x + er * NC;
 #pragma unroll
           for (int m = 0; m < NC; ++m) {
-            const double u_ = ur[m];
+            const double u_ = Ud[m];   // row r of U_i
 #pragma unroll
-            for (int c = 0; c < NC; ++c) dn[c] -= u_ * VL[(m * NC + c) * ld + er];
-            bn -= u_ * x[m * ld + er];
-          }
-          if (hrr) {
+            for (int c = 0; c < NC; ++c) dn[c] -= u_ * VLe[m * NC + c];
+            bn -= u_ * xe[m];
+            if (hrr) {
 #pragma unroll
-            for (int m = 0; m < NC; ++m) {
-              const double u_ = ur[m];
-#pragma unroll
-              for (int c = 0; c < NC; ++c) un[c] -= u_ * VU[(m * NC + c) * ld + er];
+              for (int c = 0; c < NC; ++c) un[c] -= u_ * VUe[m * NC + c];
             }
           }
         }
         if (hl) {
+          const double* Ue = U + el * BS;
+          const double* VUe = VU + el * BS;
+          const double* xe = x + el * NC;
 #pragma unroll
           for (int m = 0; m < NC; ++m) {
-            const double u_ = uc[m];
+            const double u_ = Ue[m * NC + r];   // column r of U_el = row r of U_el^T
 #pragma unroll
-            for (int c = 0; c < NC; ++c) dn[c] -= u_ * VU[(m * NC + c) * ld + el];
-            bn -= u_ * x[m * ld + el];
+            for (int c = 0; c < NC; ++c) dn[c] -= u_ * VUe[m * NC + c];
+            bn -= u_ * xe[m];
           }
         }
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { D[(r * NC + c) * ld + i] = dn[c]; U[(r * NC + c) * ld + i] = un[c]; }
-        b[r * ld + i] = bn;
+        for (int c = 0; c < NC; ++c) { Dd[c] = dn[c]; Ud[c] = un[c]; }
+        b[i * NC + r] = bn;
       }
     }
     MYR_SYNC();
     MYR_CPH(s == 1 ? 11 : (s == 2 ? 13 : 15));
   }
-  // ---- root (block 0): loads and inverse, CTA barrier, then the rows (the barrier separates reads of D_0 from writes)
+  // ---- root (block 0): every lane only reads its own row of D_0 before overwriting it
   {
-    double Dinv[BB], bi[NC];
-    if (grp == 0) {
-      pivot_rows(0, Dinv);
-#pragma unroll
-      for (int m = 0; m < NC; ++m) bi[m] = b[m * ld];
-    }
-    MYR_SYNC();
-    if (grp == 0) {
-      MYR_CR_ROWS(r) {
+#ifdef __CUDA_ARCH__
+    if (int(threadIdx.x) < 32) {   // warp 0 (group 0 lives there); the shuffles need the whole warp
+      double dr[NC];
+      pivot_row(0, grp == 0, dr);
+      if (grp == 0 && rvalid) {
+        const int r = rl;
+#else
+    {
+      double Dinv[BB];
+      pivot_full(0, Dinv);
+      for (int r = 0; r < NC; ++r) {
+        double dr[NC];
+        for (int m = 0; m < NC; ++m) dr[m] = Dinv[r * NC + m];
+#endif
         double xr = 0.0;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          double v = 0.0;
-#pragma unroll
-          for (int rr = 0; rr < NC; ++rr) v = (rr == r) ? Dinv[rr * NC + c] : v;
-          D[(r * NC + c) * ld] = v;
-          xr += v * bi[c];
-        }
-        x[r * ld] = xr;
+        for (int c = 0; c < NC; ++c) { D[r * NC + c] = dr[c]; xr += dr[c] * b[c]; }
+        x[r] = xr;
       }
     }
   }
@@ -409,22 +590,22 @@ MYR_HDI void block_cr_solve(int St, int ld, double* D, double* U, double* VL, do
     for (int k = grp; k < nodd; k += ngrp) {
       const int i = (2 * k + 1) * s;
       MYR_CR_ROWS(r) {
-        double a = x[r * ld + i];
+        double a = x[i * NC + r];
+        const double* VLd = VL + i * BS + r * NC;
+        const double* xl = x + (i - s) * NC;
 #pragma unroll
-        for (int m = 0; m < NC; ++m) a -= VL[(r * NC + m) * ld + i] * x[m * ld + (i - s)];
+        for (int m = 0; m < NC; ++m) a -= VLd[m] * xl[m];
         if (i + s < St) {
+          const double* VUd = VU + i * BS + r * NC;
+          const double* xr_ = x + (i + s) * NC;
 #pragma unroll
-          for (int m = 0; m < NC; ++m) a -= VU[(r * NC + m) * ld + i] * x[m * ld + (i + s)];
+          for (int m = 0; m < NC; ++m) a -= VUd[m] * xr_[m];
         }
-        x[r * ld + i] = a;
+        x[i * NC + r] = a;
       }
     }
     MYR_SYNC();
   }
-  npos = (int)(block_sum((double)cp, red) + 0.5);
-  nneg = (int)(block_sum((double)cn, red) + 0.5);
-  nzero = (int)(block_sum((double)cz, red) + 0.5);
-  MYR_SYNC();
 }
 
 // Re-solve with the factors left by block_cr_solve (pivot inverses in D, VL, VU) for a new right-hand side b
@@ -432,34 +613,37 @@ MYR_HDI void block_cr_solve(int St, int ld, double* D, double* U, double* VL, do
 // the elimination of e from its surviving neighbours is  b_i -= VL_e^T b_e  (right neighbour e = i+s) and
 // b_i -= VU_e^T b_e (left neighbour e = i-s), which only needs data of already-final eliminated nodes.
 template <int NC>
-MYR_HDN void block_cr_resolve(int St, int ld, const double* D, const double* VL, const double* VU, double* b, double* x) {
+MYR_HDN void block_cr_resolve(int St, const double* D, const double* VL, const double* VU, double* b, double* x) {
+  constexpr int BS = pad2(NC * NC);
   int s = 1;
   for (; s < St; s <<= 1) {
     for (int i = 2 * MYR_TID * s; i < St; i += 2 * MYR_NT * s) {
       double bn[NC];
 #pragma unroll
-      for (int r = 0; r < NC; ++r) bn[r] = b[r * ld + i];
+      for (int r = 0; r < NC; ++r) bn[r] = b[i * NC + r];
       const int er = i + s, el = i - s;
       if (er < St) {
+        const double* V = VL + er * BS;
 #pragma unroll
         for (int r = 0; r < NC; ++r) {
           double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < NC; ++k) a += VL[(k * NC + r) * ld + er] * b[k * ld + er];
+          for (int k = 0; k < NC; ++k) a += V[k * NC + r] * b[er * NC + k];
           bn[r] -= a;
         }
       }
       if (el >= 0) {
+        const double* V = VU + el * BS;
 #pragma unroll
         for (int r = 0; r < NC; ++r) {
           double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < NC; ++k) a += VU[(k * NC + r) * ld + el] * b[k * ld + el];
+          for (int k = 0; k < NC; ++k) a += V[k * NC + r] * b[el * NC + k];
           bn[r] -= a;
         }
       }
 #pragma unroll
-      for (int r = 0; r < NC; ++r) b[r * ld + i] = bn[r];
+      for (int r = 0; r < NC; ++r) b[i * NC + r] = bn[r];
     }
     MYR_SYNC();
   }
@@ -468,26 +652,29 @@ MYR_HDN void block_cr_resolve(int St, int ld, const double* D, const double* VL,
     for (int r = 0; r < NC; ++r) {
       double a = 0.0;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) a += D[(r * NC + k) * ld] * b[k * ld];
-      x[r * ld] = a;
+      for (int k = 0; k < NC; ++k) a += D[r * NC + k] * b[k];
+      x[r] = a;
     }
   }
   MYR_SYNC();
   for (s >>= 1; s >= 1; s >>= 1) {
     for (int i = (2 * MYR_TID + 1) * s; i < St; i += 2 * MYR_NT * s) {
       double xi[NC];
+      const double* Di = D + i * BS;
+      const double* VLi = VL + i * BS;
+      const double* VUi = VU + i * BS;
 #pragma unroll
       for (int r = 0; r < NC; ++r) {
         double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) a += D[(r * NC + k) * ld + i] * b[k * ld + i];
+        for (int k = 0; k < NC; ++k) a += Di[r * NC + k] * b[i * NC + k];
         xi[r] = a;
       }
 #pragma unroll
       for (int r = 0; r < NC; ++r) {
         double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) a += VL[(r * NC + k) * ld + i] * x[k * ld + (i - s)];
+        for (int k = 0; k < NC; ++k) a += VLi[r * NC + k] * x[(i - s) * NC + k];
         xi[r] -= a;
       }
       if (i + s < St) {
@@ -495,202 +682,255 @@ MYR_HDN void block_cr_resolve(int St, int ld, const double* D, const double* VL,
         for (int r = 0; r < NC; ++r) {
           double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < NC; ++k) a += VU[(r * NC + k) * ld + i] * x[k * ld + (i + s)];
+          for (int k = 0; k < NC; ++k) a += VUi[r * NC + k] * x[(i + s) * NC + k];
           xi[r] -= a;
         }
       }
 #pragma unroll
-      for (int r = 0; r < NC; ++r) x[r * ld + i] = xi[r];
+      for (int r = 0; r < NC; ++r) x[i * NC + r] = xi[r];
     }
     MYR_SYNC();
   }
 }
 
-// KKT solve for one instance:
+// J_q^T d for the two roles of node q:  u[i] = sum_r G[r][i] dp[r] + F[r][i] ds[r]
+template <class S>
+MYR_HDI void jt_times(const Problem& P, const WS<S>& ws, int q, const double* dvec /* stage-major */, double* u) {
+  using D = Dims<S>;
+  constexpr int NW = S::NW, NC = S::NC;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) u[i] = 0.0;
+  const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
+  if (jp >= 0) {
+    const double* Gq = ws.G + q * D::GS;
+#pragma unroll
+    for (int r = 0; r < NC; ++r) {
+      const double d = dvec[jp * NC + r];
+#pragma unroll
+      for (int i = 0; i < NW; ++i) u[i] += Gq[r * NW + i] * d;
+    }
+  }
+  if (js >= 0) {
+    const double* Fq = ws.F + q * D::GS;
+#pragma unroll
+    for (int r = 0; r < NC; ++r) {
+      const double d = dvec[js * NC + r];
+#pragma unroll
+      for (int i = 0; i < NW; ++i) u[i] += Fq[r * NW + i] * d;
+    }
+  }
+}
+
+// KKT factorisation + multiplier solve for one instance:
 //   [ H + Sigma + dw I   J^T ] [dz  ]     [ rb ]
 //   [ J               -dc I ] [dlam] = - [ c  ]
-// node data (G,F,W,rb) and c are in the workspace; sigma/fixed per variable via callback arrays.
-// Returns inertia-ok flag; dz (node-major) and dlam (stage-major) in the workspace.
+// node data (G, F, W, sig, rb) and c are in the slot.  Phases:
+//   (1) per node: Hinv = (W + Sigma + dw)^-1 with fixed variables removed (inertia of H), tv = Hinv rb, and the node's
+//       ROLE PRODUCTS  G Hinv G^T, F Hinv F^T (diagonal-block parts), F Hinv G^T (coupling block), G tv, F tv -- every
+//       node datum is read once and the products are formed while Hinv is still in registers;
+//   (2) per stage: sum the role products of the stage's nodes into the Schur-complement block, right-hand side;
+//   (3) block cyclic reduction -> dlam, inertia of S.
+// Returns the inertia-ok flag; minpr = smallest relative pivot of the node blocks (refinement is only worth it when small).
 template <class S>
-MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const double* sigma /*node-major*/,
-                       const uint32_t* fixmask /*per node*/, double delta_w, double delta_c, double* cr, double* red,
-                       double delta_reg = 0.0, int max_refine = 0) {
-  constexpr int NW = S::NW, NC = S::NC;
-  const int Q = L.Q, St = L.St;
+MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, double delta_c, double delta_reg, double& minpr_out,
+                        int& parity) {
+  using D = Dims<S>;
+  constexpr int NW = S::NW, NC = S::NC, BS = D::BS;
+  const int Q = ws.Q, St = ws.St;
 #if defined(MYR_PROFILE_PHASES) && defined(__CUDA_ARCH__)
   long long kph_t0_ = clock64();
 #define MYR_KPH(idx) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase_cycles[idx], (unsigned long long)(t_ - kph_t0_)); kph_t0_ = t_; } } while (0)
 #else
 #define MYR_KPH(idx) do { } while (0)
 #endif
-  // ---- node blocks: Hinv = (W + Sigma + dw)^-1 with fixed variables removed; inertia of H
-  int hp = 0, hn = 0, hz = 0;
+  // role-product slots: the k-th node block of a stage (phi_slot / psi_slot) writes into its own scratch
+  double* const slotM[3] = {ws.crD, ws.crVL, ws.crVU};
+  double* const slotV[3] = {ws.crb, ws.ct, ws.dl2};
+  int hn = 0, hz = 0;
   double minpr = INFINITY;
   for (int q = MYR_TID; q < Q; q += MYR_NT) {
-    double A[NW * NW], inv[NW * NW];
-    const CSV Wq{w + L.W + q, L.ldq};
+    double A[NW * NW], inv[NW * NW], t[NW];
+    const double* Wq = ws.W + q * D::WSZ;
 #pragma unroll
     for (int i = 0; i < NW; ++i)
 #pragma unroll
       for (int j = 0; j < NW; ++j) A[i * NW + j] = Wq[pidx(i, j, NW)];
 #pragma unroll
-    for (int i = 0; i < NW; ++i) A[i * NW + i] += sigma[q * NW + i] + delta_w + delta_reg;
+    for (int i = 0; i < NW; ++i) A[i * NW + i] += NQ(sig, q, i) + delta_w + delta_reg;
     int p_, n_, z_;
     double pr_;
-    sym_inverse<NW>(A, fixmask[q], inv, p_, n_, z_, &pr_);
+    sym_inverse<NW>(A, ws.fix()[q], inv, p_, n_, z_, &pr_);
     minpr = fmin(minpr, pr_);
-    hp += p_; hn += n_; hz += z_;
+    hn += n_; hz += z_;
+    double* Hq = ws.Hinv + q * D::HS;
 #pragma unroll
-    for (int i = 0; i < NW * NW; ++i) NQ(Hinv, q, i) = inv[i];
-  }
-  const int Hneg = (int)(block_sum((double)hn, red) + 0.5);
-  const int Hzero = (int)(block_sum((double)hz, red) + 0.5);
-  minpr = block_min(minpr, red);
-  // refinement is only worth its cost when some node block was close to singular
-  if (!(minpr < 1e-4)) max_refine = 0;
-  (void)hp;
-  MYR_SYNC();
-  MYR_KPH(6);
-  // ---- stage blocks of the Schur complement S = J Hinv J^T + dc I and its right-hand side  c - J Hinv rb
-  const int ld = L.lds;
-  double* D = cr; double* U = D + ld * NC * NC; double* VL = U + ld * NC * NC; double* VU = VL + ld * NC * NC;
-  double* bb = VU + ld * NC * NC;
-  for (int j = MYR_TID; j < St; j += MYR_NT) {
-    double Dj[NC * NC], bj[NC];
-#pragma unroll
-    for (int i = 0; i < NC * NC; ++i) Dj[i] = 0.0;
-#pragma unroll
-    for (int r = 0; r < NC; ++r) { Dj[r * NC + r] = delta_c; bj[r] = NS(c, j, r); }
-    const int nk = S::stage_nodes(P, j);
-    for (int k = 0; k < nk; ++k) {
-      int role; const int q = S::stage_node(P, j, k, role);
-      double Jq[NC * NW], Hi[NW * NW], T[NC * NW];
-      {
-        const CSV Jv{w + (role ? L.F : L.G) + q, L.ldq};
-        const CSV Hv{w + L.Hinv + q, L.ldq};
-#pragma unroll
-        for (int i = 0; i < NC * NW; ++i) Jq[i] = Jv[i];
-#pragma unroll
-        for (int i = 0; i < NW * NW; ++i) Hi[i] = Hv[i];
-      }
-      mm<NC, NW, NW>(Jq, Hi, T);
-#pragma unroll
-      for (int r = 0; r < NC; ++r) {
-#pragma unroll
-        for (int c2 = 0; c2 < NC; ++c2) {
-          double a = 0.0;
-#pragma unroll
-          for (int i = 0; i < NW; ++i) a += T[r * NW + i] * Jq[c2 * NW + i];
-          Dj[r * NC + c2] += a;
-        }
-        double a = 0.0;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) a += T[r * NW + i] * NQ(rb, q, i);
-        bj[r] -= a;
-      }
-      if (role == 1 && j + 1 < St) {  // link node: coupling to the next stage  U_j = F Hinv G^T
-        const CSV Gq{w + L.G + q, L.ldq};
-#pragma unroll
-        for (int r = 0; r < NC; ++r)
-#pragma unroll
-          for (int c2 = 0; c2 < NC; ++c2) {
-            double a = 0.0;
-#pragma unroll
-            for (int i = 0; i < NW; ++i) a += T[r * NW + i] * Gq[c2 * NW + i];
-            U[(r * NC + c2) * ld + j] = a;
-          }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < NC; ++r)
-#pragma unroll
-      for (int c2 = 0; c2 < NC; ++c2) D[(r * NC + c2) * ld + j] = 0.5 * (Dj[r * NC + c2] + Dj[c2 * NC + r]);
-#pragma unroll
-    for (int r = 0; r < NC; ++r) { bb[r * ld + j] = bj[r]; NS(sch, j, r) = bj[r] - NS(c, j, r); }
-  }
-  MYR_SYNC();
-  MYR_KPH(7);
-  int sp, sn, sz;
-  block_cr_solve<NC>(St, ld, D, U, VL, VU, bb, w + L.dlam, red, sp, sn, sz);
-  MYR_KPH(8);
-  // inertia(K) = inertia(H) + inertia(-S): correct iff  n-(S) == n-(H)  and nothing is singular
-  const bool ok = (Hzero == 0) && (sz == 0) && (sn == Hneg);
-  // ---- dz = -Hinv (rb + G^T dlam_phi + F^T dlam_psi)
-  for (int q = MYR_TID; q < Q; q += MYR_NT) {
-    double v[NW];
-#pragma unroll
-    for (int i = 0; i < NW; ++i) v[i] = NQ(rb, q, i);
-    const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-    if (jp >= 0) {
-      const CSV Gq{w + L.G + q, L.ldq};
-#pragma unroll
-      for (int r = 0; r < NC; ++r) {
-        const double d = NS(dlam, jp, r);
-#pragma unroll
-        for (int i = 0; i < NW; ++i) v[i] += Gq[r * NW + i] * d;
-      }
-    }
-    if (js >= 0) {
-      const CSV Fq{w + L.F + q, L.ldq};
-#pragma unroll
-      for (int r = 0; r < NC; ++r) {
-        const double d = NS(dlam, js, r);
-#pragma unroll
-        for (int i = 0; i < NW; ++i) v[i] += Fq[r * NW + i] * d;
-      }
-    }
-    const CSV Hi{w + L.Hinv + q, L.ldq};
+    for (int i = 0; i < NW * NW; ++i) Hq[i] = inv[i];
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
       double a = 0.0;
 #pragma unroll
-      for (int k = 0; k < NW; ++k) a += Hi[i * NW + k] * v[k];
-      NQ(dz, q, i) = -a;
+      for (int k = 0; k < NW; ++k) a += inv[i * NW + k] * NQ(rb, q, k);
+      t[i] = a;
+      NQ(tv, q, i) = a;
+    }
+    const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
+    const double* Gq = ws.G + q * D::GS;
+    const double* Fq = ws.F + q * D::GS;
+    if (jp >= 0) {
+      const int sl = S::phi_slot(P, q);
+      double* Dst = slotM[sl] + jp * BS;
+      double* vst = slotV[sl] + jp * NC;
+#pragma unroll
+      for (int r = 0; r < NC; ++r) {
+        double T[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          double a = 0.0;
+#pragma unroll
+          for (int k = 0; k < NW; ++k) a += Gq[r * NW + k] * inv[k * NW + i];
+          T[i] = a;
+        }
+#pragma unroll
+        for (int c2 = 0; c2 < NC; ++c2) {
+          double a = 0.0;
+#pragma unroll
+          for (int i = 0; i < NW; ++i) a += T[i] * Gq[c2 * NW + i];
+          Dst[r * NC + c2] = a;
+        }
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) a += Gq[r * NW + i] * t[i];
+        vst[r] = a;
+      }
+    }
+    if (js >= 0) {
+      const int sl = S::psi_slot(P, q);
+      double* Dst = slotM[sl] + js * BS;
+      double* vst = slotV[sl] + js * NC;
+      double* Ust = ws.crU + js * BS;
+      const bool link = jp >= 0;   // the node also starts the next stage: coupling block U_js = F Hinv G^T
+#pragma unroll
+      for (int r = 0; r < NC; ++r) {
+        double T[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          double a = 0.0;
+#pragma unroll
+          for (int k = 0; k < NW; ++k) a += Fq[r * NW + k] * inv[k * NW + i];
+          T[i] = a;
+        }
+#pragma unroll
+        for (int c2 = 0; c2 < NC; ++c2) {
+          double a = 0.0;
+#pragma unroll
+          for (int i = 0; i < NW; ++i) a += T[i] * Fq[c2 * NW + i];
+          Dst[r * NC + c2] = a;
+        }
+        if (link) {
+#pragma unroll
+          for (int c2 = 0; c2 < NC; ++c2) {
+            double a = 0.0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) a += T[i] * Gq[c2 * NW + i];
+            Ust[r * NC + c2] = a;
+          }
+        }
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) a += Fq[r * NW + i] * t[i];
+        vst[r] = a;
+      }
     }
   }
   MYR_SYNC();
-  // ---- iterative refinement against the matrix WITHOUT delta_reg: the node blocks are factorised with a tiny
-  // regularisation (directions in which W + Sigma is singular, e.g. a state that enters neither cost nor dynamics and is
-  // far from its bounds, would otherwise make the block elimination break down although the KKT matrix is regular);
-  // the refinement removes its effect and recovers the digits the Schur complement loses.
-  for (int itr = 0; ok && itr < max_refine; ++itr) {
+  MYR_KPH(6);
+  // ---- stage blocks of the Schur complement S = J Hinv J^T + dc I and its right-hand side  c - J Hinv rb
+  for (int j = MYR_TID; j < St; j += MYR_NT) {
+    double Dj[NC * NC], bj[NC];
+    const int nk = S::stage_nodes(P, j);
+#pragma unroll
+    for (int i = 0; i < NC * NC; ++i) Dj[i] = slotM[0][j * BS + i];
+#pragma unroll
+    for (int r = 0; r < NC; ++r) bj[r] = NS(c, j, r) - slotV[0][j * NC + r];
+    for (int k = 1; k < nk; ++k) {
+      const double* Ms = slotM[k] + j * BS;
+      const double* vs = slotV[k] + j * NC;
+#pragma unroll
+      for (int i = 0; i < NC * NC; ++i) Dj[i] += Ms[i];
+#pragma unroll
+      for (int r = 0; r < NC; ++r) bj[r] -= vs[r];
+    }
+    double* Dd = ws.crD + j * BS;
+#pragma unroll
+    for (int r = 0; r < NC; ++r)
+#pragma unroll
+      for (int c2 = 0; c2 < NC; ++c2) Dd[r * NC + c2] = 0.5 * (Dj[r * NC + c2] + Dj[c2 * NC + r]) + (r == c2 ? delta_c : 0.0);
+#pragma unroll
+    for (int r = 0; r < NC; ++r) { ws.crb[j * NC + r] = bj[r]; NS(sch, j, r) = bj[r] - NS(c, j, r); }
+  }
+  MYR_SYNC();
+  MYR_KPH(7);
+  int sp, sn, sz;
+  block_cr_solve<NC>(St, ws.crD, ws.crU, ws.crVL, ws.crVU, ws.crb, ws.dlam, sp, sn, sz);
+  MYR_KPH(8);
+  double rv[5] = {(double)hn, (double)hz, minpr, (double)sn, (double)sz};
+  block_reduce_multi<R_SUM, R_SUM, R_MIN, R_SUM, R_SUM>(rv, ws.red, parity);
+  const int Hneg = (int)(rv[0] + 0.5), Hzero = (int)(rv[1] + 0.5), Sneg = (int)(rv[3] + 0.5), Szero = (int)(rv[4] + 0.5);
+  minpr_out = rv[2];
+  // inertia(K) = inertia(H) + inertia(-S): correct iff  n-(S) == n-(H)  and nothing is singular
+  return (Hzero == 0) && (Szero == 0) && (Sneg == Hneg);
+}
+
+// dz = -(tv + Hinv J^T dl) for the multiplier step dl (stage-major), tv = Hinv rb; written to the node vector dst
+template <class S>
+MYR_HDI void kkt_backsub(const Problem& P, const WS<S>& ws, const double* dl, double* dst) {
+  using D = Dims<S>;
+  constexpr int NW = S::NW;
+  for (int q = MYR_TID; q < ws.Q; q += MYR_NT) {
+    double u[NW];
+    jt_times<S>(P, ws, q, dl, u);
+    const double* Hq = ws.Hinv + q * D::HS;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      double a = NQ(tv, q, i);
+#pragma unroll
+      for (int k = 0; k < NW; ++k) a += Hq[i * NW + k] * u[k];
+      dst[i * ws.ldq + q] = -a;
+    }
+  }
+}
+
+// Iterative refinement against the matrix WITHOUT delta_reg: the node blocks are factorised with a tiny
+// regularisation (directions in which W + Sigma is singular, e.g. a state that enters neither cost nor dynamics and is
+// far from its bounds, would otherwise make the block elimination break down although the KKT matrix is regular);
+// the refinement removes its effect and recovers the digits the Schur complement loses.  Scratch: dzL (node residual),
+// dl2 (multiplier correction), crb.
+template <class S>
+MYR_HDI void kkt_refine(const Problem& P, const WS<S>& ws, double delta_w, double delta_c, int max_refine, int& parity) {
+  using D = Dims<S>;
+  constexpr int NW = S::NW, NC = S::NC;
+  const int Q = ws.Q, St = ws.St;
+  for (int itr = 0; itr < max_refine; ++itr) {
     // node residual  rz = -rb - (H dz + G^T dlam_phi + F^T dlam_psi)   (stored in dzL), norms
     double rmax = 0.0, smax = 0.0;
     for (int q = MYR_TID; q < Q; q += MYR_NT) {
-      double v[NW], d[NW];
+      double v[NW], d[NW], u[NW];
 #pragma unroll
       for (int i = 0; i < NW; ++i) { v[i] = -NQ(rb, q, i); d[i] = NQ(dz, q, i); smax = fmax(smax, fabs(v[i])); }
-      const CSV Wq{w + L.W + q, L.ldq};
+      const double* Wq = ws.W + q * D::WSZ;
 #pragma unroll
       for (int i = 0; i < NW; ++i) {
-        double a = (sigma[q * NW + i] + delta_w) * d[i];
+        double a = (NQ(sig, q, i) + delta_w) * d[i];
 #pragma unroll
         for (int k = 0; k < NW; ++k) a += Wq[pidx(i, k, NW)] * d[k];
         v[i] -= a;
       }
-      const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-      if (jp >= 0) {
-        const CSV Gq{w + L.G + q, L.ldq};
-#pragma unroll
-        for (int r = 0; r < NC; ++r) {
-          const double dl = NS(dlam, jp, r);
-#pragma unroll
-          for (int i = 0; i < NW; ++i) v[i] -= Gq[r * NW + i] * dl;
-        }
-      }
-      if (js >= 0) {
-        const CSV Fq{w + L.F + q, L.ldq};
-#pragma unroll
-        for (int r = 0; r < NC; ++r) {
-          const double dl = NS(dlam, js, r);
-#pragma unroll
-          for (int i = 0; i < NW; ++i) v[i] -= Fq[r * NW + i] * dl;
-        }
-      }
+      jt_times<S>(P, ws, q, ws.dlam, u);
+      const uint32_t fm = ws.fix()[q];
 #pragma unroll
       for (int i = 0; i < NW; ++i) {
-        const bool fx = (fixmask[q] >> i) & 1u;
-        const double r_ = fx ? 0.0 : v[i];
+        const bool fx = (fm >> i) & 1u;
+        const double r_ = fx ? 0.0 : v[i] - u[i];
         NQ(dzL, q, i) = r_;
         rmax = fmax(rmax, (r_ != r_) ? INFINITY : fabs(r_));
       }
@@ -704,14 +944,14 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
       const int nk = S::stage_nodes(P, j);
       for (int k = 0; k < nk; ++k) {
         int role; const int q = S::stage_node(P, j, k, role);
-        const CSV Jq{w + (role ? L.F : L.G) + q, L.ldq};
-        const CSV Hi{w + L.Hinv + q, L.ldq};
+        const double* Jq = (role ? ws.F : ws.G) + q * D::GS;
+        const double* Hq = ws.Hinv + q * D::HS;
         double t[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
           double a = 0.0;
 #pragma unroll
-          for (int k2 = 0; k2 < NW; ++k2) a += Hi[i * NW + k2] * NQ(dzL, q, k2);
+          for (int k2 = 0; k2 < NW; ++k2) a += Hq[i * NW + k2] * NQ(dzL, q, k2);
           t[i] = a;
         }
 #pragma unroll
@@ -725,96 +965,55 @@ MYR_HDI bool kkt_solve(const Problem& P, const Layout<S>& L, double* w, const do
 #pragma unroll
       for (int r = 0; r < NC; ++r) {
         rmax = fmax(rmax, (rc[r] != rc[r]) ? INFINITY : fabs(rc[r]));
-        bb[r * ld + j] = bj[r] - rc[r];
+        ws.crb[j * NC + r] = bj[r] - rc[r];
       }
     }
-    rmax = block_max(rmax, red);
-    smax = block_max(smax, red);
-    MYR_SYNC();
+    double rv[2] = {rmax, smax};
+    block_reduce_multi<R_MAX, R_MAX>(rv, ws.red, parity);   // its barrier also publishes crb
+    rmax = rv[0]; smax = rv[1];
     if (!(rmax > 1e-13 * fmax(1.0, smax)) || !isfinite(rmax)) break;
-    block_cr_resolve<NC>(St, ld, D, VL, VU, bb, w + L.dzU /* ddlam: lds*NC <= ldq*NW */);
-    for (int j = MYR_TID; j < St; j += MYR_NT)
-#pragma unroll
-      for (int r = 0; r < NC; ++r) NS(dlam, j, r) += NS(dzU, j, r);
+    block_cr_resolve<NC>(St, ws.crD, ws.crVL, ws.crVU, ws.crb, ws.dl2);
+    for (int k = MYR_TID; k < St * NC; k += MYR_NT) ws.dlam[k] += ws.dl2[k];
     for (int q = MYR_TID; q < Q; q += MYR_NT) {
-      double v[NW];
+      double v[NW], u[NW];
+      jt_times<S>(P, ws, q, ws.dl2, u);
 #pragma unroll
-      for (int i = 0; i < NW; ++i) v[i] = NQ(dzL, q, i);
-      const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-      if (jp >= 0) {
-        const CSV Gq{w + L.G + q, L.ldq};
-#pragma unroll
-        for (int r = 0; r < NC; ++r) {
-          const double d = NS(dzU, jp, r);
-#pragma unroll
-          for (int i = 0; i < NW; ++i) v[i] -= Gq[r * NW + i] * d;
-        }
-      }
-      if (js >= 0) {
-        const CSV Fq{w + L.F + q, L.ldq};
-#pragma unroll
-        for (int r = 0; r < NC; ++r) {
-          const double d = NS(dzU, js, r);
-#pragma unroll
-          for (int i = 0; i < NW; ++i) v[i] -= Fq[r * NW + i] * d;
-        }
-      }
-      const CSV Hi{w + L.Hinv + q, L.ldq};
+      for (int i = 0; i < NW; ++i) v[i] = NQ(dzL, q, i) - u[i];
+      const double* Hq = ws.Hinv + q * D::HS;
 #pragma unroll
       for (int i = 0; i < NW; ++i) {
         double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < NW; ++k) a += Hi[i * NW + k] * v[k];
+        for (int k = 0; k < NW; ++k) a += Hq[i * NW + k] * v[k];
         NQ(dz, q, i) += a;
       }
     }
     MYR_SYNC();
   }
-  return ok;
+}
+
+// complete KKT solve (factor, multipliers, primal step, optional refinement): what myr_kkt_solve exposes
+template <class S>
+MYR_HDI bool kkt_solve(const Problem& P, const WS<S>& ws, double delta_w, double delta_c, double delta_reg, int max_refine, int& parity) {
+  double minpr;
+  const bool ok = kkt_factor<S>(P, ws, delta_w, delta_c, delta_reg, minpr, parity);
+  if (!ok) return false;
+  kkt_backsub<S>(P, ws, ws.dlam, ws.dz);
+  MYR_SYNC();
+  // refinement is only worth its cost when some node block was close to singular
+  if (max_refine > 0 && minpr < 1e-4) kkt_refine<S>(P, ws, delta_w, delta_c, max_refine, parity);
+  return true;
 }
 
 // Second-order-correction solve (IPOPT A-5.5 ff.) with the factors the last kkt_solve left behind: same matrix,
 // constraint right-hand side csoc instead of c.   S dl2 = csoc - J Hinv rb,   dz2 = -Hinv (rb + J^T dl2).
 template <class S>
-MYR_HDN void kkt_soc_solve(const Problem& P, const Layout<S>& L, double* w, double* cr) {
-  constexpr int NW = S::NW, NC = S::NC;
-  const int Q = L.Q, St = L.St, ld = L.lds;
-  double* D = cr; double* VL = D + 2 * ld * NC * NC; double* VU = VL + ld * NC * NC;
-  double* bb = VU + ld * NC * NC;
-  for (int j = MYR_TID; j < St; j += MYR_NT)
-#pragma unroll
-    for (int r = 0; r < NC; ++r) bb[r * ld + j] = NS(csoc, j, r) + NS(sch, j, r);
+MYR_HDN void kkt_soc_solve(const Problem& P, const WS<S>& ws) {
+  constexpr int NC = S::NC;
+  for (int k = MYR_TID; k < ws.St * NC; k += MYR_NT) ws.crb[k] = ws.csoc[k] + ws.sch[k];
   MYR_SYNC();
-  block_cr_resolve<NC>(St, ld, D, VL, VU, bb, w + L.dl2);
-  for (int q = MYR_TID; q < Q; q += MYR_NT) {
-    double v[NW];
-#pragma unroll
-    for (int i = 0; i < NW; ++i) v[i] = NQ(rb, q, i);
-    const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-    if (jp >= 0) {
-#pragma unroll
-      for (int r = 0; r < NC; ++r) {
-        const double d = NS(dl2, jp, r);
-#pragma unroll
-        for (int i = 0; i < NW; ++i) v[i] += NQ(G, q, r * NW + i) * d;
-      }
-    }
-    if (js >= 0) {
-#pragma unroll
-      for (int r = 0; r < NC; ++r) {
-        const double d = NS(dl2, js, r);
-#pragma unroll
-        for (int i = 0; i < NW; ++i) v[i] += NQ(F, q, r * NW + i) * d;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      double a = 0.0;
-#pragma unroll
-      for (int k = 0; k < NW; ++k) a += NQ(Hinv, q, i * NW + k) * v[k];
-      NQ(dz2, q, i) = -a;
-    }
-  }
+  block_cr_resolve<NC>(ws.St, ws.crD, ws.crVL, ws.crVU, ws.crb, ws.dl2);
+  kkt_backsub<S>(P, ws, ws.dl2, ws.dz2);
   MYR_SYNC();
 }
 
@@ -832,35 +1031,23 @@ struct IpmIO {
   double* con_inf;    // [B]  max |c|
   int32_t* status;    // [B]
   int32_t* iters;     // [B]
-  double* work;       // [B][work_stride]
-  long long work_stride;
 };
 
 // per-instance pointers of the NLP the IPM iterates on (the reference NLP itself for collocation, the lifted one for
-// shooting); nv / ncn are that NLP's sizes
+// shooting), in that NLP's flat layouts (S::zidx / S::cidx); nv / ncn are that NLP's sizes
 struct InstPtrs {
   const double* z0; const double* lb; const double* ub;
   double* z; double* lam; double* zL; double* zU;
-  double* w;
   int nv, ncn;
 };
 struct InstResult { double f, E0, cinf; int status, iters; };
 
 template <class S>
-MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const InstPtrs& ip, double* cr, double* red,
-                                      double* sig_sh /*Q*NW doubles*/, uint32_t* fix_sh /*Q*/, double* mlp_scr = nullptr) {
+MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const InstPtrs& ip, const WS<S>& ws) {
   constexpr int NW = S::NW, NC = S::NC;
-  const Layout<S> L(P);
-  const int Q = L.Q, St = L.St;
-  const int ncn = ip.ncn;
-  double* w = ip.w;
-  double* z = ip.z;
-  double* lam = ip.lam;
-  double* zL = ip.zL;
-  double* zU = ip.zU;
-  const double* lb = ip.lb;
-  const double* ub = ip.ub;
-  const double* z0 = ip.z0;
+  const int Q = ws.Q, St = ws.St;
+  const int ncn = St * NC;
+  int parity = 0;
 
   // ---- initial point: push into the (relaxed) box, unit bound multipliers, zero lambda
   for (int q = MYR_TID; q < Q; q += MYR_NT) {
@@ -868,9 +1055,10 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
       const int id = S::zidx(P, q, i);
-      const Bnd bd = make_bnd(lb[id], ub[id], O.bound_relax);
-      double x = z0[id];
-      if (bd.fixed) { x = lb[id]; fm |= (1u << i); }
+      const double lb = ip.lb[id], ub = ip.ub[id];
+      const Bnd bd = make_bnd(lb, ub, O.bound_relax);
+      double x = ip.z0[id];
+      if (bd.fixed) { x = lb; fm |= (1u << i); }
       else {
         if (bd.hasL) {
           double pL = O.bound_push * fmax(1.0, fabs(bd.lbr));
@@ -883,15 +1071,15 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
           x = fmin(x, bd.ubr - pU);
         }
       }
-      z[id] = x;
-      zL[id] = bd.hasL ? 1.0 : 0.0;
-      zU[id] = bd.hasU ? 1.0 : 0.0;
-      NQ(lbr, q, i) = bd.fixed ? lb[id] : (bd.hasL ? bd.lbr : -INFINITY);
-      NQ(ubr, q, i) = bd.fixed ? lb[id] : (bd.hasU ? bd.ubr : INFINITY);
+      NQ(z, q, i) = x;
+      NQ(zL, q, i) = bd.hasL ? 1.0 : 0.0;
+      NQ(zU, q, i) = bd.hasU ? 1.0 : 0.0;
+      NQ(lbr, q, i) = bd.fixed ? lb : (bd.hasL ? bd.lbr : -INFINITY);
+      NQ(ubr, q, i) = bd.fixed ? lb : (bd.hasU ? bd.ubr : INFINITY);
     }
-    fix_sh[q] = fm;
+    ws.fix()[q] = fm;
   }
-  for (int k = MYR_TID; k < ncn; k += MYR_NT) lam[k] = 0.0;
+  for (int k = MYR_TID; k < ncn; k += MYR_NT) ws.lam[k] = 0.0;
   MYR_SYNC();
 
   MYR_PH_DECL
@@ -902,53 +1090,39 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
   const double mu_floor = fmax(O.mu_min, O.tol / 10.0);
 
   while (true) {
-    // ---------------- K1: evaluate with derivatives
+    // ---------------- K1: evaluate with derivatives; rb = grad f + J^T lam
     MYR_PH(9);
-    f = eval_nodes<S, 2>(P, L, z, lam, w, red, mlp_scr);
-    stage_constraints<S>(P, L, w, w + L.c, red, cinf, c1);
+    double fpart = eval_nodes<S, 2>(P, ws, ws.z);
+    MYR_SYNC();
     MYR_PH(0);
-    // ---------------- dual residual, complementarity, scaling sums
-    // (per-variable loops are deliberately NOT unrolled: the body is long and the kernel is instruction-fetch bound)
+    // ---------------- constraints, dual residual, complementarity, scaling sums: one fused reduction
+    double cmx = 0.0, csm = 0.0, suml = 0.0;
+    stage_constraints<S>(P, ws, ws.c, cmx, csm);
+    for (int k = MYR_TID; k < ncn; k += MYR_NT) suml += fabs(ws.lam[k]);
     double rdmax = 0.0, szmax = -INFINITY, szmin = INFINITY, sumz = 0.0, nbnd = 0.0, slog = 0.0;
     for (int q = MYR_TID; q < Q; q += MYR_NT) {
-      const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-      double lp[NC], ls[NC];
-#pragma unroll
-      for (int rr = 0; rr < NC; ++rr) {
-        lp[rr] = jp >= 0 ? lam[S::cidx(P, jp, rr)] : 0.0;
-        ls[rr] = js >= 0 ? lam[S::cidx(P, js, rr)] : 0.0;
-      }
-      const uint32_t fm = fix_sh[q];
+      const uint32_t fm = ws.fix()[q];
       LogProd lpq;
-#pragma unroll 1
-      for (int i = 0; i < NW; ++i) {
-        const int id = S::zidx(P, q, i);
-        double r = NQ(gl, q, i);
 #pragma unroll
-        for (int rr = 0; rr < NC; ++rr) r += NQ(G, q, rr * NW + i) * lp[rr] + NQ(F, q, rr * NW + i) * ls[rr];
+      for (int i = 0; i < NW; ++i) {
         const bool fixed = (fm >> i) & 1u;
         double rd = 0.0;
         if (!fixed) {
-          const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = z[id], zl = zL[id], zu = zU[id];
-          rd = r - zl + zu;
+          const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = NQ(z, q, i), zl = NQ(zL, q, i), zu = NQ(zU, q, i);
+          rd = NQ(rb, q, i) - zl + zu;
           if (lo > -INFINITY) { const double sl = x - lo; const double pz = sl * zl; szmax = fmax(szmax, pz); szmin = fmin(szmin, pz); sumz += zl; nbnd += 1.0; lpq.mul(sl); }
           if (hi < INFINITY) { const double su = hi - x; const double pz = su * zu; szmax = fmax(szmax, pz); szmin = fmin(szmin, pz); sumz += zu; nbnd += 1.0; lpq.mul(su); }
         }
-        NQ(rb, q, i) = fixed ? 0.0 : r;  // grad f + J^T lam (barrier terms added after mu is known)
         const double a = (rd != rd) ? INFINITY : fabs(rd);
         rdmax = fmax(rdmax, a);
       }
       slog += lpq.value();
     }
-    double suml = 0.0;
-    for (int k = MYR_TID; k < ncn; k += MYR_NT) suml += fabs(lam[k]);
-    rdmax = block_max(rdmax, red);
-    szmax = block_max(szmax, red);
-    szmin = block_min(szmin, red);
-    sumz = block_sum(sumz, red);
-    nbnd = block_sum(nbnd, red);
-    slog = block_sum(slog, red);
-    suml = block_sum(suml, red);
+    {
+      double rv[10] = {fpart, cmx, csm, rdmax, szmax, szmin, sumz, nbnd, slog, suml};
+      block_reduce_multi<R_SUM, R_MAX, R_SUM, R_MAX, R_MAX, R_MIN, R_SUM, R_SUM, R_SUM, R_SUM>(rv, ws.red, parity);
+      f = rv[0]; cinf = rv[1]; c1 = rv[2]; rdmax = rv[3]; szmax = rv[4]; szmin = rv[5]; sumz = rv[6]; nbnd = rv[7]; slog = rv[8]; suml = rv[9];
+    }
     const double sd = fmax(O.s_max, (suml + sumz) / fmax(1.0, (double)ncn + nbnd)) / O.s_max;
     const double sc = nbnd > 0 ? fmax(O.s_max, sumz / nbnd) / O.s_max : 1.0;
     // lifted shooting: step defects accumulate along an interval's rollout, so the per-step feasibility tolerance is
@@ -969,23 +1143,22 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     MYR_PH(1);
     // ---------------- barrier gradient rb and Sigma (reciprocal slacks are kept for the step-size phase)
     for (int q = MYR_TID; q < Q; q += MYR_NT) {
-      const uint32_t fm = fix_sh[q];
-#pragma unroll 1
+      const uint32_t fm = ws.fix()[q];
+#pragma unroll
       for (int i = 0; i < NW; ++i) {
-        const int id = S::zidx(P, q, i);
         const bool fixed = (fm >> i) & 1u;
         double sg = 0.0, rbv = NQ(rb, q, i), r1 = 0.0, r2 = 0.0;
         if (!fixed) {
-          const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = z[id];
-          if (lo > -INFINITY) { r1 = 1.0 / (x - lo); sg += zL[id] * r1; rbv -= mu * r1; }
-          if (hi < INFINITY) { r2 = 1.0 / (hi - x); sg += zU[id] * r2; rbv += mu * r2; }
+          const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = NQ(z, q, i);
+          if (lo > -INFINITY) { r1 = 1.0 / (x - lo); sg += NQ(zL, q, i) * r1; rbv -= mu * r1; }
+          if (hi < INFINITY) { r2 = 1.0 / (hi - x); sg += NQ(zU, q, i) * r2; rbv += mu * r2; }
         }
         NQ(rsl, q, i) = r1; NQ(rsu, q, i) = r2;
-        sig_sh[q * NW + i] = sg;
+        NQ(sig, q, i) = sg;
         NQ(rb, q, i) = fixed ? 0.0 : rbv;
       }
     }
-    MYR_SYNC();
+    // (no barrier: the node phase of kkt_factor reads sig / rb of the thread's own nodes)
 
     MYR_PH(2);
     // ---------------- K2: KKT solve with inertia correction (IPOPT Algorithm IC)
@@ -993,7 +1166,7 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     bool ok = false;
     for (int tries = 0; tries < 60; ++tries) {
       // accurate steps only matter near the solution: refine the linear solve in the end game only
-      ok = kkt_solve<S>(P, L, w, sig_sh, fix_sh, delta, O.delta_c, cr, red, O.delta_reg, E0 < 1e-3 ? O.max_refine : 0);
+      ok = kkt_solve<S>(P, ws, delta, O.delta_c, O.delta_reg, E0 < 1e-3 ? O.max_refine : 0, parity);
       if (ok) break;
       if (delta == 0.0) delta = (delta_last == 0.0) ? O.delta_0 : fmax(O.delta_min, O.kappa_w_minus * delta_last);
       else delta *= (delta_last == 0.0) ? O.kappa_w_plus_first : O.kappa_w_plus;
@@ -1007,43 +1180,29 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     // alpha = min(1, tau / max_i(-d_i / slack_i)): one division at the end instead of one per variable
     double m_pr = 0.0, m_du = 0.0, dphi = 0.0, dHd = 0.0;
     for (int q = MYR_TID; q < Q; q += MYR_NT) {
-      const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-      double lp[NC], ls[NC], dp[NC], ds[NC];
+      double jt[NW];
+      jt_times<S>(P, ws, q, ws.dlam, jt);
+      const uint32_t fm = ws.fix()[q];
 #pragma unroll
-      for (int rr = 0; rr < NC; ++rr) {
-        lp[rr] = jp >= 0 ? lam[S::cidx(P, jp, rr)] : 0.0;
-        ls[rr] = js >= 0 ? lam[S::cidx(P, js, rr)] : 0.0;
-        dp[rr] = jp >= 0 ? NS(dlam, jp, rr) : 0.0;
-        ds[rr] = js >= 0 ? NS(dlam, js, rr) : 0.0;
-      }
-      const uint32_t fm = fix_sh[q];
-#pragma unroll 1
       for (int i = 0; i < NW; ++i) {
-        const int id = S::zidx(P, q, i);
         const bool fixed = (fm >> i) & 1u;
-        // J^T (lam + dlam) part of  H dz = -(rb + J^T dlam): dz^T H dz = -dz.(rb + J^T dlam)
-        double jt = 0.0, jl = 0.0;
-#pragma unroll
-        for (int rr = 0; rr < NC; ++rr) {
-          const double g = NQ(G, q, rr * NW + i), f_ = NQ(F, q, rr * NW + i);
-          jt += g * dp[rr] + f_ * ds[rr];
-          jl += g * lp[rr] + f_ * ls[rr];
-        }
         const double d = NQ(dz, q, i);
         double dl = 0.0, du = 0.0;
         if (!fixed) {
           const double rbv = NQ(rb, q, i);
-          dHd -= d * (rbv + jt);
-          dphi += d * (rbv - jl);  // barrier-objective gradient = rb - J^T lam
+          // H dz = -(rb + J^T dlam):  dz^T H dz = -dz.(rb + J^T dlam)
+          dHd -= d * (rbv + jt[i]);
           const double r1 = NQ(rsl, q, i), r2 = NQ(rsu, q, i);
+          // barrier-objective gradient = grad f - mu / s_L + mu / s_U
+          dphi += d * (NQ(gl, q, i) - mu * r1 + mu * r2);
           if (r1 != 0.0) {
-            const double zl = zL[id];
+            const double zl = NQ(zL, q, i);
             dl = mu * r1 - zl - zl * r1 * d;
             m_pr = fmax(m_pr, -d * r1);
             if (dl < 0.0) m_du = fmax(m_du, -dl / zl);
           }
           if (r2 != 0.0) {
-            const double zu = zU[id];
+            const double zu = NQ(zU, q, i);
             du = mu * r2 - zu + zu * r2 * d;
             m_pr = fmax(m_pr, d * r2);
             if (du < 0.0) m_du = fmax(m_du, -du / zu);
@@ -1053,10 +1212,11 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
         NQ(dzU, q, i) = du;
       }
     }
-    m_pr = block_max(m_pr, red);
-    m_du = block_max(m_du, red);
-    dphi = block_sum(dphi, red);
-    dHd = block_sum(dHd, red);
+    {
+      double rv[4] = {m_pr, m_du, dphi, dHd};
+      block_reduce_multi<R_MAX, R_MAX, R_SUM, R_SUM>(rv, ws.red, parity);
+      m_pr = rv[0]; m_du = rv[1]; dphi = rv[2]; dHd = rv[3];
+    }
     if (!(dphi == dphi)) { status = ST_NAN; break; }
     const double a_pr = m_pr > tau ? tau / m_pr : 1.0;
     const double a_du = m_du > tau ? tau / m_du : 1.0;
@@ -1071,7 +1231,6 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     const double phi0 = f - mu * slog + nu * c1;
     double alpha = a_pr;
     bool accepted = false;
-    double* zt = w + L.zt;
     double f_t = 0.0;
     // Armijo with IPOPT's rounding-error relaxation (10 eps |phi|) so that converged iterates are not rejected by cancellation
     const double armijo_slack = 10.0 * 2.220446049250313e-16 * fabs(phi0);
@@ -1082,31 +1241,32 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     double a2 = 1.0, c1_prev = 0.0;
     while (ls < O.max_ls) {
       if (soc) {
-        kkt_soc_solve<S>(P, L, w, cr);
+        kkt_soc_solve<S>(P, ws);
         double m2 = 0.0;
         for (int q = MYR_TID; q < Q; q += MYR_NT) {
-#pragma unroll 1
+#pragma unroll
           for (int i = 0; i < NW; ++i) {
             const double d = NQ(dz2, q, i);
             m2 = fmax(m2, fmax(-d * NQ(rsl, q, i), d * NQ(rsu, q, i)));
           }
         }
-        m2 = block_max(m2, red);
+        double rv[1] = {m2};
+        block_reduce_multi<R_MAX>(rv, ws.red, parity);
+        m2 = rv[0];
         a2 = m2 > tau ? tau / m2 : 1.0;
       }
       const double a = soc ? a2 : alpha;
-      const int step_off = soc ? L.dz2 : L.dz;
+      const double* step = soc ? ws.dz2 : ws.dz;
       ls_used = ls;
       // ---- trial point z + a * step, its barrier log-sum, objective and constraints
       double blog = 0.0;
       for (int q = MYR_TID; q < Q; q += MYR_NT) {
-        const uint32_t fm = fix_sh[q];
+        const uint32_t fm = ws.fix()[q];
         LogProd lpq;
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < NW; ++i) {
-          const int id = S::zidx(P, q, i);
-          const double x = z[id] + a * w[step_off + i * L.ldq + q];
-          zt[id] = x;
+          const double x = NQ(z, q, i) + a * step[i * ws.ldq + q];
+          NQ(zt, q, i) = x;
           if (!((fm >> i) & 1u)) {
             const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i);
             if (lo > -INFINITY) lpq.mul(x - lo);
@@ -1115,11 +1275,17 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
         }
         blog += lpq.value();
       }
+      // (no barrier: eval_nodes reads the trial point of the thread's own nodes -- except the cooperative MLP pass)
+      if (Layout<S>::kCoopMlp) MYR_SYNC();
+      const double ft_part = eval_nodes<S, 0>(P, ws, ws.zt);
       MYR_SYNC();
-      f_t = eval_nodes<S, 0>(P, L, zt, lam, w, red, mlp_scr);
-      double ci_t, c1_t;
-      stage_constraints<S>(P, L, w, w + L.ct, red, ci_t, c1_t);
-      blog = block_sum(blog, red);
+      double ci_t = 0.0, c1_t = 0.0;
+      stage_constraints<S>(P, ws, ws.ct, ci_t, c1_t);
+      {
+        double rv[4] = {ft_part, ci_t, c1_t, blog};
+        block_reduce_multi<R_SUM, R_MAX, R_SUM, R_SUM>(rv, ws.red, parity);
+        f_t = rv[0]; ci_t = rv[1]; c1_t = rv[2]; blog = rv[3];
+      }
       const double phit = f_t - mu * blog + nu * c1_t;
       if (isfinite(phit) && phit <= phi0 + O.eta * alpha * Dm + armijo_slack) { accepted = true; break; }
       if (!soc) {
@@ -1130,9 +1296,7 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
         // behaved instances (the bulk of a batch) an unconditional SOC costs more re-solves than it saves iterations
         // (CARTPOLE N=100: -12 % iterations, +16 % time), on the hard ones it is what makes the method converge.
         if (ls == 0 && soc_armed && O.max_soc > 0 && c1_t >= c1) {
-          for (int j = MYR_TID; j < St; j += MYR_NT)
-#pragma unroll
-            for (int r = 0; r < NC; ++r) NS(csoc, j, r) = alpha * NS(c, j, r) + NS(ct, j, r);
+          for (int k = MYR_TID; k < ncn; k += MYR_NT) ws.csoc[k] = alpha * ws.c[k] + ws.ct[k];
           MYR_SYNC();
           soc = true; ks = 0; c1_prev = c1_t;
           continue;
@@ -1142,16 +1306,13 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
         // kappa_soc: the correction must keep reducing the infeasibility, at most max_soc times
         if (!(c1_t <= 0.99 * c1_prev) || ++ks >= O.max_soc) { soc = false; alpha *= 0.5; ++ls; continue; }
         c1_prev = c1_t;
-        for (int j = MYR_TID; j < St; j += MYR_NT)
-#pragma unroll
-          for (int r = 0; r < NC; ++r) NS(csoc, j, r) = a2 * NS(csoc, j, r) + NS(ct, j, r);
+        for (int k = MYR_TID; k < ncn; k += MYR_NT) ws.csoc[k] = a2 * ws.csoc[k] + ws.ct[k];
         MYR_SYNC();
       }
     }
+    const double* dl_acc = ws.dlam;
     if (accepted && soc) {  // the multiplier step of the corrected system goes with the corrected primal step
-      for (int j = MYR_TID; j < St; j += MYR_NT)
-#pragma unroll
-        for (int r = 0; r < NC; ++r) NS(dlam, j, r) = NS(dl2, j, r);
+      dl_acc = ws.dl2;
       alpha = a2;
     }
     hard_iters = ls_used >= 4 ? hard_iters + 1 : 0;
@@ -1164,34 +1325,43 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     MYR_PH(5);
     // ---------------- accept: primal, equality multipliers, bound multipliers (with the kappa_sigma safeguard)
     for (int q = MYR_TID; q < Q; q += MYR_NT) {
-      const uint32_t fm = fix_sh[q];
-#pragma unroll 1
+      const uint32_t fm = ws.fix()[q];
+#pragma unroll
       for (int i = 0; i < NW; ++i) {
         if ((fm >> i) & 1u) continue;
-        const int id = S::zidx(P, q, i);
-        const double x = zt[id];
-        z[id] = x;
+        const double x = NQ(zt, q, i);
+        NQ(z, q, i) = x;
         const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i);
         if (lo > -INFINITY) {
           const double ms = mu / (x - lo);
-          double v = zL[id] + a_du * NQ(dzL, q, i);
+          double v = NQ(zL, q, i) + a_du * NQ(dzL, q, i);
           v = fmax(fmin(v, O.kappa_sigma * ms), ms / O.kappa_sigma);
-          zL[id] = v;
+          NQ(zL, q, i) = v;
         }
         if (hi < INFINITY) {
           const double ms = mu / (hi - x);
-          double v = zU[id] + a_du * NQ(dzU, q, i);
+          double v = NQ(zU, q, i) + a_du * NQ(dzU, q, i);
           v = fmax(fmin(v, O.kappa_sigma * ms), ms / O.kappa_sigma);
-          zU[id] = v;
+          NQ(zU, q, i) = v;
         }
       }
     }
-    for (int j = MYR_TID; j < St; j += MYR_NT)
-#pragma unroll
-      for (int r = 0; r < NC; ++r) lam[S::cidx(P, j, r)] += alpha * NS(dlam, j, r);
+    for (int k = MYR_TID; k < ncn; k += MYR_NT) ws.lam[k] += alpha * dl_acc[k];
     MYR_SYNC();
     ++it;
   }
+  // ---- results in the NLP's flat layouts
+  for (int q = MYR_TID; q < Q; q += MYR_NT) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      const int id = S::zidx(P, q, i);
+      ip.z[id] = NQ(z, q, i); ip.zL[id] = NQ(zL, q, i); ip.zU[id] = NQ(zU, q, i);
+    }
+  }
+  for (int j = MYR_TID; j < St; j += MYR_NT)
+#pragma unroll
+    for (int r = 0; r < NC; ++r) ip.lam[S::cidx(P, j, r)] = NS(lam, j, r);
+  MYR_SYNC();
   InstResult res;
   res.f = f; res.E0 = E0; res.cinf = cinf; res.status = status; res.iters = it;
   return res;
@@ -1200,12 +1370,11 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
 // Collocation: the IPM works directly on the caller's arrays.
 template <class S>
 MYR_HDI typename std::enable_if<!scheme_is_lifted<S>::value>::type
-ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, double* cr, double* red, double* sig_sh, uint32_t* fix_sh,
-                double* mlp_scr = nullptr) {
+ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, const WS<S>& ws) {
   const long long nv = P.nvars, nc = P.ncon;
   InstPtrs ip{io.z0 + b * nv, io.lb + b * nv, io.ub + b * nv, io.z + b * nv, io.lam + b * nc, io.zL + b * nv, io.zU + b * nv,
-              io.work + (long long)b * io.work_stride, P.nvars, P.ncon};
-  const InstResult r = ipm_solve_instance<S>(P, O, ip, cr, red, sig_sh, fix_sh, mlp_scr);
+              P.nvars, P.ncon};
+  const InstResult r = ipm_solve_instance<S>(P, O, ip, ws);
   if (MYR_TID == 0) {
     io.obj[b] = r.f; io.kkt_err[b] = r.E0; io.con_inf[b] = r.cinf; io.status[b] = r.status; io.iters[b] = r.iters;
   }
@@ -1215,15 +1384,12 @@ ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, doub
 // objective / constraint violation of the REFERENCE NLP (rollouts from the interval-start states).
 template <class S>
 MYR_HDI typename std::enable_if<scheme_is_lifted<S>::value>::type
-ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, double* cr, double* red, double* sig_sh, uint32_t* fix_sh,
-                double* = nullptr) {
+ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, const WS<S>& ws) {
   constexpr int n = S::n, m = S::m, NW = S::NW, NC = S::NC;
-  const Layout<S> L(P);
-  const int Q = L.Q, St = L.St;
+  const int Q = ws.Q, St = ws.St;
   const int nvI = Q * NW, ncI = St * NC;
   const long long nv = P.nvars, nc = P.ncon;
-  double* w = io.work + (long long)b * io.work_stride;
-  double* zI0 = w + L.ext; double* lbI = zI0 + nvI; double* ubI = lbI + nvI; double* zI = ubI + nvI;
+  double* zI0 = ws.ext; double* lbI = zI0 + nvI; double* ubI = lbI + nvI; double* zI = ubI + nvI;
   double* zLI = zI + nvI; double* zUI = zLI + nvI; double* lamI = zUI + nvI;
   const double* z0 = io.z0 + b * nv; const double* lb = io.lb + b * nv; const double* ub = io.ub + b * nv;
   // ---- expansion: real variables copy guess and bounds; copies / hidden states are free
@@ -1264,8 +1430,8 @@ ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, doub
   MYR_SYNC();
   Problem Pi = P;
   Pi.nvars = nvI; Pi.ncon = ncI;
-  InstPtrs ip{zI0, lbI, ubI, zI, lamI, zLI, zUI, w, nvI, ncI};
-  InstResult r = ipm_solve_instance<S>(Pi, O, ip, cr, red, sig_sh, fix_sh);
+  InstPtrs ip{zI0, lbI, ubI, zI, lamI, zLI, zUI, nvI, ncI};
+  InstResult r = ipm_solve_instance<S>(Pi, O, ip, ws);
   MYR_SYNC();
   // ---- map back
   double* z = io.z + b * nv; double* lam = io.lam + b * nc; double* zL = io.zL + b * nv; double* zU = io.zU + b * nv;
@@ -1295,10 +1461,12 @@ ipm_solve_entry(const Problem& P, const IpmOpts& O, const IpmIO& io, int b, doub
 #pragma unroll
     for (int i = 0; i < n; ++i) { const double d = px[i] - z[(k + 1) * n + i]; cm = fmax(cm, (d != d) ? INFINITY : fabs(d)); }
   }
-  fs = block_sum(fs, red);
-  cm = block_max(cm, red);
+  int parity = 0;
+  double rv[2] = {fs, cm};
+  block_reduce_multi<R_SUM, R_MAX>(rv, ws.red, parity);
+  MYR_SYNC();
   if (MYR_TID == 0) {
-    io.obj[b] = fs; io.kkt_err[b] = r.E0; io.con_inf[b] = cm; io.status[b] = r.status; io.iters[b] = r.iters;
+    io.obj[b] = rv[0]; io.kkt_err[b] = r.E0; io.con_inf[b] = rv[1]; io.status[b] = r.status; io.iters[b] = r.iters;
   }
 }
 

@@ -7,6 +7,9 @@
 
 #include <string>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../../include/myriad_b200.h"
 #include "engine.cuh"
@@ -129,7 +132,13 @@ int sys_problem_sizes(const MyrDesc* desc, MyrSizes* out) {
     out->n = S::n; out->m = S::m;
     out->nvars = P.nvars; out->ncon = P.ncon;
     out->nodes = L.Q; out->stages = L.St; out->nw = S::NW; out->nc = S::NC;
-    out->ipm_workspace_doubles = L.total;
+    {  // a workspace SLOT with every array in global memory (what the host twin uses; the device kernels place the
+       // hot arrays in shared memory and use less): callers size the workspace with this upper bound
+      int sm, gl;
+      L.place(0, sm, gl);
+      out->ipm_workspace_doubles = gl;
+      out->ipm_workspace_slots = MYR_WS_MAX_SLOTS;
+    }
     if (scheme_is_lifted<S>::value) {
       const int mc = P.method == RK4 ? 2 : 1;
       out->nx_nodes = P.N + 1; out->nu_nodes = mc * P.N * P.cpi + 1;
@@ -190,6 +199,18 @@ __global__ void shooting_eval_kernel(Problem P, const double* z, double* f, doub
   const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pair < (long long)P.B * P.N) shooting_eval_pair<Sys, NU>(P, pair, z, f, grad, c, J, nullptr);
 }
+
+// views of the reference's flat layouts for the cooperative MLP pass
+template <class S>
+struct RefZView {
+  const Problem* P; const double* z;
+  MYR_HDI double operator()(int q, int i) const { return z[S::zidx(*P, q, i)]; }
+};
+template <class S>
+struct RefLamView {
+  const Problem* P; const double* lam;
+  MYR_HDI double operator()(int j, int r) const { return lam ? lam[S::cidx(*P, j, r)] : 0.0; }
+};
 
 // ------------------------------------------------------------------ K1 kernel
 // One CTA per instance, one thread per node.  phi/psi meet in shared memory to form the stage constraints;
@@ -303,8 +324,10 @@ __global__ void __launch_bounds__(EvalLaunch<S>::kThreads, EvalLaunch<S>::kMinBl
     double fsum = 0.0;
     if constexpr (Layout<S>::kCoopMlp) {
       double* df = sDyn; double* dJ = df + Q * S::n; double* dH = dJ + Q * S::n * NW;
-      if (want_h) mlp_nodes_pass<S, 2>(P, Q, z, lam, df, dJ, dH, sScr);
-      else mlp_nodes_pass<S, 1>(P, Q, z, lam, df, dJ, dH, sScr);
+      const RefZView<S> zv{&P, z};
+      const RefLamView<S> lv{&P, lam};
+      if (want_h) mlp_nodes_pass<S, 2>(P, Q, zv, lv, df, dJ, dH, sScr);
+      else mlp_nodes_pass<S, 1>(P, Q, zv, lv, df, dJ, dH, sScr);
     }
     for (int q = threadIdx.x; q < Q; q += blockDim.x) {
       double v[NW], lp[NC], ls[NC];
@@ -409,8 +432,9 @@ int sys_eval(const MyrDesc* desc, int B, const double* z, const double* lam, dou
     size_t smd = 64 + 2 * (size_t)L.Q * S::NC + (Jblk ? (size_t)L.St * row : 0) + ((lam && Hblk) ? (size_t)L.Q * S::NWP : 0);
     if (Layout<S>::kCoopMlp) smd += (size_t)L.Q * (S::n + S::n * S::NW + S::NWP) + mlp_scratch_doubles<S>(P.mlp);
     const size_t sm = smd * sizeof(double);
-    if (sm > 200 * 1024) return fail(MYR_E_UNSUPPORTED, "problem too large for the shared-memory staged K1 (%s%lld bytes)", "", (long long)sm);
-    if (sm > 48 * 1024) cudaFuncSetAttribute(eval_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (sm > 227 * 1024) return fail(MYR_E_UNSUPPORTED, "problem too large for the shared-memory staged K1 (%s%lld bytes)", "", (long long)sm);
+    if (sm > 48 * 1024 && cudaFuncSetAttribute(eval_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+      return fail(MYR_E_CUDA, "myr_eval: cannot reserve %s%lld bytes of shared memory", "", (long long)sm);
     eval_kernel<S><<<B, EvalLaunch<S>::threads(L.Q), sm, (cudaStream_t)stream>>>(P, z, lam, f, grad, c, Jblk, Hblk);
     return cuda_check("myr_eval");
   });
@@ -441,79 +465,132 @@ int sys_host_eval(const MyrDesc* desc, int B, const double* z, const double* lam
   });
 }
 
+// ------------------------------------------------------------------ workspace slots and shared-memory plan
+// Launch shape of the per-instance kernels: persistent CTAs, one instance at a time each; 128 threads stride over
+// nodes / stages (256 for the cooperative tensor-core MLP pass of NODE systems and for the 3-node stages of
+// Hermite-Simpson).  kMinBlocks bounds registers so that several instances are resident per SM: the kernel is
+// latency-bound, resident warps are what hides it.
+#ifndef MYR_IPM_MINBLOCKS
+#define MYR_IPM_MINBLOCKS 2
+#endif
+#ifndef MYR_IPM_THREADS
+#define MYR_IPM_THREADS 128
+#endif
+template <class S>
+struct IpmLaunch {
+  static constexpr bool kWide = Layout<S>::kCoopMlp || S::kMaxStageNodes >= 3;
+  static constexpr int kThreads = kWide ? 256 : MYR_IPM_THREADS;
+  static constexpr int kMinBlocks = kWide ? 1 : MYR_IPM_MINBLOCKS;
+  static int threads(int Q) { const int t = threads_for(Q, Layout<S>::kCoopMlp); return t < kThreads ? t : kThreads; }
+};
+
+// Which arrays of the slot live in shared memory (engine.cuh, "Memory plan") and how many CTAs per SM that allows.
+// sm_100: 228 KB of shared memory per SM, 227 KB per CTA at most, 1 KB reserved per resident CTA.
+template <class S>
+struct SlotPlan {
+  unsigned long long mask;
+  int smem_doubles, glob_doubles, ctas_per_sm;
+  size_t fixed_bytes, smem_bytes;
+  explicit SlotPlan(const Problem& P, int max_ctas) {
+    const Layout<S> L(P);
+    const size_t mlp = Layout<S>::kCoopMlp ? (size_t)mlp_scratch_doubles<S>(P.mlp) * sizeof(double) : 0;
+    fixed_bytes = 2 * kRedStride * sizeof(double) + mlp;
+    auto budget = [&](int k) -> long long {
+      long long per = 233472 / k - 1024;
+      if (per > 232448) per = 232448;
+      if (const char* e = getenv("MYR_IPM_SMEM_KB")) { const long long cap = atoll(e) * 1024; if (cap < per) per = cap; }
+      per -= (long long)fixed_bytes;
+      return per > 0 ? per / (long long)sizeof(double) : 0;
+    };
+    int k = max_ctas < 1 ? 1 : max_ctas;
+    if (const char* e = getenv("MYR_IPM_CTAS")) { if (atoi(e) >= 1) k = atoi(e); }   // tuning knob (debug)
+    else {
+      // the cyclic-reduction scratch is what shared memory is for: give up resident CTAs until it fits
+      int kk = k;
+      while (kk > 1 && budget(kk) < L.cr_doubles()) --kk;
+      if (budget(kk) >= L.cr_doubles()) k = kk;
+    }
+    ctas_per_sm = k;
+    mask = L.place(budget(k), smem_doubles, glob_doubles);
+    smem_bytes = fixed_bytes + (size_t)smem_doubles * sizeof(double);
+  }
+};
+
+static int device_sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 1) sms = 1;
+  }
+  return sms;
+}
+
+// grid of a persistent per-instance kernel: resident CTAs of the device, at most one per instance / workspace slot
+template <class K>
+static int persistent_grid(K kernel, int threads, size_t smem, int B, int* err) {
+  *err = 0;
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { *err = 1; return 0; }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) { *err = 1; return 0; }
+  long long g = (long long)occ * device_sm_count();
+  if (g > MYR_WS_MAX_SLOTS) g = MYR_WS_MAX_SLOTS;
+  if (g > B) g = B;
+  return (int)g;
+}
+
 // ------------------------------------------------------------------ K2 kernel
 template <class S>
 __host__ __device__ inline void kkt_instance(const Problem& P, int b, const double* Hblk, const double* Jblk, const double* sigma,
                                              const double* rhs_z, const double* rhs_c, double dw, double dc, double* dz, double* dlam,
-                                             int32_t* inertia_ok, double* work, long long stride, double* cr, double* red,
-                                             double* sig_sh, uint32_t* fix_sh) {
-  const Layout<S> L(P);
-  double* w = work + (long long)b * stride;
-  const long long jstride = (long long)L.St * S::kMaxStageNodes * S::NC * S::NW;
+                                             int32_t* inertia_ok, const WS<S>& ws) {
+  using D = Dims<S>;
+  constexpr int NW = S::NW, NC = S::NC;
+  const long long jstride = (long long)ws.St * S::kMaxStageNodes * NC * NW;
   const double* Jb = Jblk + (long long)b * jstride;
-  for (int q = MYR_TID; q < L.Q; q += MYR_NT) {
+  for (int q = MYR_TID; q < ws.Q; q += MYR_NT) {
     const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-    for (int i = 0; i < S::NC * S::NW; ++i) {
-      NQ(G, q, i) = jp >= 0 ? Jb[((long long)jp * S::kMaxStageNodes + S::phi_slot(P, q)) * S::NC * S::NW + i] : 0.0;
-      NQ(F, q, i) = js >= 0 ? Jb[((long long)js * S::kMaxStageNodes + S::psi_slot(P, q)) * S::NC * S::NW + i] : 0.0;
+    double* Gq = ws.G + q * D::GS; double* Fq = ws.F + q * D::GS; double* Wq = ws.W + q * D::WSZ;
+    for (int i = 0; i < NC * NW; ++i) {
+      Gq[i] = jp >= 0 ? Jb[((long long)jp * S::kMaxStageNodes + S::phi_slot(P, q)) * NC * NW + i] : 0.0;
+      Fq[i] = js >= 0 ? Jb[((long long)js * S::kMaxStageNodes + S::psi_slot(P, q)) * NC * NW + i] : 0.0;
     }
-    for (int i = 0; i < S::NWP; ++i) NQ(W, q, i) = Hblk[((long long)b * L.Q + q) * S::NWP + i];
+    for (int i = 0; i < S::NWP; ++i) Wq[i] = Hblk[((long long)b * ws.Q + q) * S::NWP + i];
     uint32_t fm = 0;
-    for (int i = 0; i < S::NW; ++i) {
+    for (int i = 0; i < NW; ++i) {
       const int id = S::zidx(P, q, i);
       const double sg = sigma[(long long)b * P.nvars + id];
       const bool fx = isinf(sg);
       if (fx) fm |= 1u << i;
-      sig_sh[q * S::NW + i] = fx ? 0.0 : sg;
+      NQ(sig, q, i) = fx ? 0.0 : sg;
       NQ(rb, q, i) = fx ? 0.0 : rhs_z[(long long)b * P.nvars + id];
     }
-    fix_sh[q] = fm;
+    ws.fix()[q] = fm;
   }
-  for (int j = MYR_TID; j < L.St; j += MYR_NT)
-    for (int r = 0; r < S::NC; ++r) NS(c, j, r) = rhs_c[(long long)b * P.ncon + S::cidx(P, j, r)];
+  for (int j = MYR_TID; j < ws.St; j += MYR_NT)
+    for (int r = 0; r < NC; ++r) NS(c, j, r) = rhs_c[(long long)b * P.ncon + S::cidx(P, j, r)];
   MYR_SYNC();
-  const bool ok = kkt_solve<S>(P, L, w, sig_sh, fix_sh, dw, dc, cr, red);
-  for (int q = MYR_TID; q < L.Q; q += MYR_NT)
-    for (int i = 0; i < S::NW; ++i) dz[(long long)b * P.nvars + S::zidx(P, q, i)] = NQ(dz, q, i);
-  for (int j = MYR_TID; j < L.St; j += MYR_NT)
-    for (int r = 0; r < S::NC; ++r) dlam[(long long)b * P.ncon + S::cidx(P, j, r)] = NS(dlam, j, r);
+  int parity = 0;
+  const bool ok = kkt_solve<S>(P, ws, dw, dc, 0.0, 0, parity);
+  for (int q = MYR_TID; q < ws.Q; q += MYR_NT)
+    for (int i = 0; i < NW; ++i) dz[(long long)b * P.nvars + S::zidx(P, q, i)] = ok ? NQ(dz, q, i) : 0.0;
+  for (int j = MYR_TID; j < ws.St; j += MYR_NT)
+    for (int r = 0; r < NC; ++r) dlam[(long long)b * P.ncon + S::cidx(P, j, r)] = NS(dlam, j, r);
   if (MYR_TID == 0 && inertia_ok) inertia_ok[b] = ok ? 1 : 0;
+  MYR_SYNC();
 }
-
-// shared-memory carve-up shared by the KKT and IPM kernels
-template <class S>
-struct SmemPlan {
-  size_t red, sig, fix, cr, mlp, total;
-  bool cr_in_smem;
-  explicit SmemPlan(const Problem& P, size_t budget = 226 * 1024) {  // 227 KB is the per-CTA maximum on sm_100
-    const Layout<S> L(P);
-    red = 64 * sizeof(double);
-    sig = (size_t)L.Q * S::NW * sizeof(double);
-    fix = (((size_t)L.Q * sizeof(uint32_t)) + 15) & ~(size_t)15;
-    cr = (size_t)L.cr_doubles() * sizeof(double);
-    cr_in_smem = red + sig + fix + cr <= budget;
-    // the MLP pass's scratch (NODE systems) sits behind the CR scratch: the CR factors must survive the line-search
-    // evaluations (second-order-correction re-solves)
-    mlp = Layout<S>::kCoopMlp ? (size_t)mlp_scratch_doubles<S>(P.mlp) * sizeof(double) : 0;
-    total = red + sig + fix + (cr_in_smem ? cr : 0) + mlp;
-  }
-};
 
 template <class S>
 __global__ void __launch_bounds__(256) kkt_kernel(Problem P, const double* Hblk, const double* Jblk, const double* sigma, const double* rhs_z,
                                                   const double* rhs_c, double dw, double dc, double* dz, double* dlam, int32_t* inertia_ok,
-                                                  double* work, long long stride, int cr_in_smem) {
-  extern __shared__ double smem[];
+                                                  unsigned long long mask, double* work, long long slot_stride) {
+  extern __shared__ __align__(16) double smem[];
   const Layout<S> L(P);
-  double* red = smem;
-  double* sig = red + 64;
-  uint32_t* fix = reinterpret_cast<uint32_t*>(sig + L.Q * S::NW);
-  double* crs = reinterpret_cast<double*>(reinterpret_cast<char*>(fix) + ((((size_t)L.Q * sizeof(uint32_t)) + 15) & ~(size_t)15));
-  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
-    double* cr = cr_in_smem ? crs : work + (long long)b * stride + L.crD;
-    kkt_instance<S>(P, b, Hblk, Jblk, sigma, rhs_z, rhs_c, dw, dc, dz, dlam, inertia_ok, work, stride, cr, red, sig, fix);
-    __syncthreads();
-  }
+  WS<S> ws(L, mask, smem + 2 * kRedStride, work + (long long)blockIdx.x * slot_stride);
+  ws.red = smem;
+  for (int b = blockIdx.x; b < P.B; b += gridDim.x)
+    kkt_instance<S>(P, b, Hblk, Jblk, sigma, rhs_z, rhs_c, dw, dc, dz, dlam, inertia_ok, ws);
 }
 
 template <class Sys>
@@ -524,13 +601,36 @@ int sys_kkt_solve(const MyrDesc* desc, int B, const double* Hblk, const double* 
     using S = decltype(s);
     if (B == 0) return (int)MYR_OK;
     const Layout<S> L(P);
-    if (ws_doubles < (size_t)B * L.total) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)B * L.total);
-    const SmemPlan<S> sp(P);
-    if (sp.total > 48 * 1024) cudaFuncSetAttribute(kkt_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
-    kkt_kernel<S><<<B, threads_for(L.Q), sp.total, (cudaStream_t)stream>>>(P, Hblk, Jblk, sigma, rhs_z, rhs_c, delta_w, delta_c, dz, dlam,
-                                                                            inertia_ok, ws, L.total, sp.cr_in_smem ? 1 : 0);
+    SlotPlan<S> sp(P, 1);
+    sp.smem_bytes -= sp.fixed_bytes - 2 * kRedStride * sizeof(double);   // no MLP scratch in this kernel
+    const int threads = threads_for(L.Q);
+    int err;
+    const int grid = persistent_grid(kkt_kernel<S>, threads, sp.smem_bytes, B, &err);
+    if (err) return fail(MYR_E_CUDA, "myr_kkt_solve: cannot configure the kernel (%s%lld bytes of shared memory)", "", (long long)sp.smem_bytes);
+    const size_t need = MYR_WS_HEADER + (size_t)grid * sp.glob_doubles;
+    if (ws_doubles < need) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)need);
+    kkt_kernel<S><<<grid, threads, sp.smem_bytes, (cudaStream_t)stream>>>(P, Hblk, Jblk, sigma, rhs_z, rhs_c, delta_w, delta_c, dz, dlam,
+                                                                          inertia_ok, sp.mask, ws + MYR_WS_HEADER, sp.glob_doubles);
     return cuda_check("myr_kkt_solve");
   });
+}
+
+// host twins: one slot (all arrays in "global" memory) per OpenMP thread, instances shared dynamically
+template <class S>
+static int host_slots(const Problem& P, int B, size_t ws_doubles, int& stride) {
+  const Layout<S> L(P);
+  int sm;
+  L.place(0, sm, stride);
+  int nt = 1;
+#ifdef _OPENMP
+  nt = omp_get_max_threads();
+#endif
+  if (nt > B) nt = B;
+  if (nt > MYR_WS_MAX_SLOTS) nt = MYR_WS_MAX_SLOTS;
+  if (nt < 1) nt = 1;
+  while (nt > 1 && MYR_WS_HEADER + (size_t)nt * stride > ws_doubles) --nt;
+  if (MYR_WS_HEADER + (size_t)nt * stride > ws_doubles) return 0;
+  return nt;
 }
 
 template <class Sys>
@@ -539,13 +639,20 @@ int sys_host_kkt_solve(const MyrDesc* desc, int B, const double* Hblk, const dou
                                   int32_t* inertia_ok, double* ws, size_t ws_doubles) {
   return dispatch_scheme<Sys>(desc, B, [&](auto s, const Problem& P) {
     using S = decltype(s);
+    if (B == 0) return (int)MYR_OK;
     const Layout<S> L(P);
-    if (ws_doubles < (size_t)B * L.total) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)B * L.total);
-    std::vector<double> red(64), sig((size_t)L.Q * S::NW);
-    std::vector<uint32_t> fix(L.Q);
-    for (int b = 0; b < B; ++b)
-      kkt_instance<S>(P, b, Hblk, Jblk, sigma, rhs_z, rhs_c, delta_w, delta_c, dz, dlam, inertia_ok, ws, L.total, ws + (long long)b * L.total + L.crD,
-                      red.data(), sig.data(), fix.data());
+    int stride;
+    const int nt = host_slots<S>(P, B, ws_doubles, stride);
+    if (!nt) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)(MYR_WS_HEADER + stride));
+#pragma omp parallel for schedule(dynamic) num_threads(nt)
+    for (int b = 0; b < B; ++b) {
+      int t = 0;
+#ifdef _OPENMP
+      t = omp_get_thread_num();
+#endif
+      WS<S> w(L, 0ull, nullptr, ws + MYR_WS_HEADER + (size_t)t * stride);
+      kkt_instance<S>(P, b, Hblk, Jblk, sigma, rhs_z, rhs_c, delta_w, delta_c, dz, dlam, inertia_ok, w);
+    }
     return (int)MYR_OK;
   });
 }
@@ -573,34 +680,23 @@ inline IpmOpts make_opts(const MyrIpmOpts* o) {
   return r;
 }
 
-// Launch shape of the per-instance interior-point kernel: one CTA per instance; 128 threads stride over nodes / stages
-// (256 for the cooperative tensor-core MLP pass of NODE systems).  kMinBlocks bounds registers so that several
-// instances are resident per SM: the kernel is latency-bound, resident warps are what hides it.
-#ifndef MYR_IPM_MINBLOCKS
-#define MYR_IPM_MINBLOCKS 2
-#endif
+// Persistent CTAs: each pulls the next instance from a counter (instances differ in iteration count, so a static
+// assignment would leave SMs idle at the tail) and solves it in its own workspace slot.
 template <class S>
-struct IpmLaunch {
-  // Hermite-Simpson has 2N+1 nodes and 2n-row stages: its CR scratch does not fit shared memory next to a second
-  // CTA anyway, so it runs 256 threads with the full register file
-  static constexpr bool kWide = Layout<S>::kCoopMlp || S::kMaxStageNodes >= 3;
-  static constexpr int kThreads = kWide ? 256 : 128;
-  static constexpr int kMinBlocks = kWide ? 1 : MYR_IPM_MINBLOCKS;
-  static int threads(int Q) { const int t = threads_for(Q, Layout<S>::kCoopMlp); return t < kThreads ? t : kThreads; }
-};
-
-template <class S>
-__global__ void __launch_bounds__(IpmLaunch<S>::kThreads, IpmLaunch<S>::kMinBlocks) ipm_kernel(Problem P, IpmOpts O, IpmIO io, int cr_in_smem) {
-  extern __shared__ double smem[];
+__global__ void __launch_bounds__(IpmLaunch<S>::kThreads, IpmLaunch<S>::kMinBlocks)
+ipm_kernel(Problem P, IpmOpts O, IpmIO io, unsigned long long mask, int smem_doubles, double* work, long long slot_stride, int* counter) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int s_next;
   const Layout<S> L(P);
-  double* red = smem;
-  double* sig = red + 64;
-  uint32_t* fix = reinterpret_cast<uint32_t*>(sig + L.Q * S::NW);
-  double* crs = reinterpret_cast<double*>(reinterpret_cast<char*>(fix) + ((((size_t)L.Q * sizeof(uint32_t)) + 15) & ~(size_t)15));
-  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
-    double* cr = cr_in_smem ? crs : io.work + (long long)b * io.work_stride + L.crD;
-    ipm_solve_entry<S>(P, O, io, b, cr, red, sig, fix, cr_in_smem ? crs + L.cr_doubles() : crs);
+  WS<S> ws(L, mask, smem + 2 * kRedStride, work + (long long)blockIdx.x * slot_stride);
+  ws.red = smem;
+  ws.mlp_scr = smem + 2 * kRedStride + smem_doubles;
+  while (true) {
+    if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
     __syncthreads();
+    const int b = s_next;
+    if (b >= P.B) break;
+    ipm_solve_entry<S>(P, O, io, b, ws);   // ends with a barrier: s_next is not overwritten before every thread has read it
   }
 }
 
@@ -614,12 +710,19 @@ int sys_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const doub
     if (!z0 || !lb || !ub || !z || !lam || !zL || !zU || !obj || !kkt_err || !con_inf || !status || !iters || !ws)
       return fail(MYR_E_BADARG, "null buffer passed to myr_ipm_solve%s", "");
     const Layout<S> L(P);
-    if (ws_doubles < (size_t)B * L.total) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)B * L.total);
-    IpmIO io{z0, lb, ub, z, lam, zL, zU, obj, kkt_err, con_inf, status, iters, ws, (long long)L.total};
+    const SlotPlan<S> sp(P, IpmLaunch<S>::kMinBlocks);
+    const int threads = IpmLaunch<S>::threads(L.Q);
+    int err;
+    const int grid = persistent_grid(ipm_kernel<S>, threads, sp.smem_bytes, B, &err);
+    if (err) return fail(MYR_E_CUDA, "myr_ipm_solve: cannot configure the kernel (%s%lld bytes of shared memory)", "", (long long)sp.smem_bytes);
+    const size_t need = MYR_WS_HEADER + (size_t)grid * sp.glob_doubles;
+    if (ws_doubles < need) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)need);
+    IpmIO io{z0, lb, ub, z, lam, zL, zU, obj, kkt_err, con_inf, status, iters};
     const IpmOpts O = make_opts(opts);
-    const SmemPlan<S> sp(P);
-    if (sp.total > 48 * 1024) cudaFuncSetAttribute(ipm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
-    ipm_kernel<S><<<B, IpmLaunch<S>::threads(L.Q), sp.total, (cudaStream_t)stream>>>(P, O, io, sp.cr_in_smem ? 1 : 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(ws, 0, MYR_WS_HEADER * sizeof(double), st) != cudaSuccess) return cuda_check("myr_ipm_solve(memset)");
+    ipm_kernel<S><<<grid, threads, sp.smem_bytes, st>>>(P, O, io, sp.mask, sp.smem_doubles, ws + MYR_WS_HEADER, sp.glob_doubles,
+                                                         reinterpret_cast<int*>(ws));
     return cuda_check("myr_ipm_solve");
   });
 }
@@ -640,14 +743,22 @@ int sys_host_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const
                                   int32_t* status, int32_t* iters, double* ws, size_t ws_doubles) {
   return dispatch_any<Sys>(desc, B, [&](auto s, const Problem& P) {
     using S = decltype(s);
+    if (B == 0) return (int)MYR_OK;
     const Layout<S> L(P);
-    if (ws_doubles < (size_t)B * L.total) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)B * L.total);
-    IpmIO io{z0, lb, ub, z, lam, zL, zU, obj, kkt_err, con_inf, status, iters, ws, (long long)L.total};
+    int stride;
+    const int nt = host_slots<S>(P, B, ws_doubles, stride);
+    if (!nt) return fail(MYR_E_WORKSPACE, "workspace too small: need %s%lld doubles", "", (long long)(MYR_WS_HEADER + stride));
+    IpmIO io{z0, lb, ub, z, lam, zL, zU, obj, kkt_err, con_inf, status, iters};
     const IpmOpts O = make_opts(opts);
-    std::vector<double> red(64), sig((size_t)L.Q * S::NW);
-    std::vector<uint32_t> fix(L.Q);
-    for (int b = 0; b < B; ++b)
-      ipm_solve_entry<S>(P, O, io, b, ws + (long long)b * L.total + L.crD, red.data(), sig.data(), fix.data());
+#pragma omp parallel for schedule(dynamic) num_threads(nt)
+    for (int b = 0; b < B; ++b) {
+      int t = 0;
+#ifdef _OPENMP
+      t = omp_get_thread_num();
+#endif
+      WS<S> w(L, 0ull, nullptr, ws + MYR_WS_HEADER + (size_t)t * stride);
+      ipm_solve_entry<S>(P, O, io, b, w);
+    }
     return (int)MYR_OK;
   });
 }

@@ -216,8 +216,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 // (mu per node from S::node_mu and the multipliers lam).  Outputs: dynf [Q][n], dynJ [Q][n][NW], dynH [Q][NWP].
 // scr: mlp_scratch_doubles<S>() doubles of shared memory.  Must be called by all threads of the CTA
 // (blockDim.x multiple of 32; hidden widths <= 16 * warps).
-template <class S, int MODE>
-__device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const double* z, const double* lam, double* dynf, double* dynJ,
+// z(q, i): variable i of node q; lam(j, r): multiplier of row r of stage j (views over the caller's layout)
+template <class S, int MODE, class ZView, class LamView>
+__device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const ZView z, const LamView lam, double* dynf, double* dynJ,
                                             double* dynH, double* scr) {
 #ifdef __CUDA_ARCH__
   constexpr int NW = S::NW, n = S::n, NWP = S::NWP;
@@ -239,7 +240,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const doubl
     for (int e = tid; e < Kin * 8; e += blockDim.x) {
       const int i = e >> 3, col = e & 7;
       const int q = min(q0 + col, Q - 1);
-      in0[e] = i < NW ? z[S::zidx(P, q, i)] : 0.0;
+      in0[e] = i < NW ? z(q, i) : 0.0;
     }
     if (MODE == 2) {
       if (tid < 8) {

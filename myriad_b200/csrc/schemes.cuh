@@ -63,10 +63,12 @@ struct Trapezoid {
 
   // weights of the dynamics Hessians in the node's Lagrangian block: mu_i = d (lam . c) / d f_i(v_q);
   // lam = the instance's multipliers in the reference's constraint order
-  MYR_HDI static void node_mu(const Problem& P, int q, const double* lam, double* mu) {
+  // lam(j, r): multiplier of row r of stage j
+  template <class LamView>
+  MYR_HDI static void node_mu(const Problem& P, int q, const LamView& lam, double* mu) {
     const double hh = 0.5 * P.h;
 #pragma unroll
-    for (int i = 0; i < n; ++i) mu[i] = hh * ((q < P.N ? lam[q * n + i] : 0.0) + (q >= 1 ? lam[(q - 1) * n + i] : 0.0));
+    for (int i = 0; i < n; ++i) mu[i] = hh * ((q < P.N ? lam(q, i) : 0.0) + (q >= 1 ? lam(q - 1, i) : 0.0));
   }
 
   template <int MODE>
@@ -164,7 +166,8 @@ struct HermiteSimpson {
   MYR_HDI static int phi_slot(const Problem&, int q) { return q & 1; }
   MYR_HDI static int psi_slot(const Problem&, int) { return 2; }
 
-  MYR_HDI static void node_mu(const Problem& P, int q, const double* lam, double* mu) {
+  template <class LamView>
+  MYR_HDI static void node_mu(const Problem& P, int q, const LamView& lam, double* mu) {
     const double h = P.h;
     const bool mid = (q & 1);
     const bool has_phi = q < 2 * P.N, has_psi = (!mid) && q >= 2;
@@ -172,8 +175,8 @@ struct HermiteSimpson {
 #pragma unroll
     for (int i = 0; i < n; ++i) {
       double a = 0.0;
-      if (has_phi) a += (mid ? -4.0 * h / 6.0 : -h / 6.0) * lam[cidx(P, jp, i)] + (mid ? 0.0 : -h / 8.0) * lam[cidx(P, jp, n + i)];
-      if (has_psi) a += (-h / 6.0) * lam[cidx(P, js, i)] + (h / 8.0) * lam[cidx(P, js, n + i)];
+      if (has_phi) a += (mid ? -4.0 * h / 6.0 : -h / 6.0) * lam(jp, i) + (mid ? 0.0 : -h / 8.0) * lam(jp, n + i);
+      if (has_psi) a += (-h / 6.0) * lam(js, i) + (h / 8.0) * lam(js, n + i);
       mu[i] = a;
     }
   }

@@ -74,7 +74,7 @@ class Engine:
     return out
 
   def workspace(self, B: int, device) -> torch.Tensor:
-    need = B * self.sizes.ipm_workspace_doubles
+    need = ML.workspace_doubles(self.sizes, B)
     if self._ws is None or self._ws.numel() < need or self._ws.device != device:
       self._ws = torch.empty(need, dtype=torch.float64, device=device)
     return self._ws

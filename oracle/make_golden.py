@@ -116,6 +116,8 @@ SOLVE_CASES = [
   "t_simplecase_hs_50", "s_vanderpol_trap_20", "s_cancer_trap_20", "s_cartpole_trap_10",
   "t_simplecase_shooting_20x3_heun", "s_vanderpol_hs_10", "n_node_cartpole_trap_10",
   "x_mould_trap_10", "x_glucose_trap_10", "x_seir_trap_10", "x_hiv_trap_10", "x_bacteria_trap_10", "x_bacteria_shooting_3x5_heun", "x_tumour_trap_10", "x_predprey_shooting_100x1_heun", "x_bear_trap_10", "x_bear_shooting_3x4_heun",  "x_harvest_trap_10", "x_scwb_shooting_4x5_heun",
+  # full-size BASELINE configs whose reference solve takes tens of minutes under the shim (generated once, round 2)
+  "c2_cartpole_hs_100", "c5_node_cartpole_trap_100",
 ]
 
 

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol(ML):
   lib = ML.lib()
   for name in declared:
     assert getattr(lib, name) is not None
-  assert lib.myr_abi_version() == 2
+  assert lib.myr_abi_version() == ML.ABI_VERSION
 
 
 @pytest.mark.parametrize("case", sorted(CASES))
@@ -131,7 +131,7 @@ def _host_ipm(ML, d, s, z0, lb, ub, max_iter=1000):
   B = z0.shape[0]
   out = dict(z=np.zeros((B, s.nvars)), lam=np.zeros((B, s.ncon)), zL=np.zeros((B, s.nvars)), zU=np.zeros((B, s.nvars)),
              obj=np.zeros(B), kkt=np.zeros(B), cinf=np.zeros(B), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32))
-  ws = np.zeros(B * s.ipm_workspace_doubles)
+  ws = np.zeros(ML.workspace_doubles(s, B))
   o = ML.MyrIpmOpts(); o.max_iter = max_iter
   ML.check(ML.lib().myr_host_ipm_solve(C.byref(d), C.byref(o), B, p(z0), p(lb), p(ub), p(out["z"]), p(out["lam"]), p(out["zL"]), p(out["zU"]),
                                        p(out["obj"]), p(out["kkt"]), p(out["cinf"]), p(out["status"]), p(out["iters"]), p(ws), ws.size))
@@ -178,7 +178,7 @@ def test_host_twin_kkt_matches_dense_numpy(ML):
   sigma = rng.uniform(0.1, 2.0, s.nvars)
   sig_in = np.where(fixed, np.inf, sigma)[None].copy()
   rz = rng.standard_normal((1, s.nvars)); rc = rng.standard_normal((1, s.ncon))
-  dz = np.zeros((1, s.nvars)); dl = np.zeros((1, s.ncon)); ok = np.zeros(1, np.int32); ws = np.zeros(s.ipm_workspace_doubles)
+  dz = np.zeros((1, s.nvars)); dl = np.zeros((1, s.ncon)); ok = np.zeros(1, np.int32); ws = np.zeros(ML.workspace_doubles(s, 1))
   for delta_w in (0.0, 5.0):
     ML.check(ML.lib().myr_host_kkt_solve(C.byref(d), 1, p(H), p(J), p(sig_in), p(rz), p(rc), delta_w, 0.0, p(dz), p(dl), p(ok), p(ws), ws.size))
     n, m, Q, nw = s.n, s.m, s.nodes, s.nw

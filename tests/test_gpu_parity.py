@@ -153,7 +153,7 @@ def test_device_matches_host_twin(case):
   z0 = np.ascontiguousarray(fx["guess"][None]); lb = np.ascontiguousarray(fx["bounds"][None, :, 0]); ub = np.ascontiguousarray(fx["bounds"][None, :, 1])
   zo = np.zeros((1, s.nvars)); lo = np.zeros((1, s.ncon)); zL = np.zeros((1, s.nvars)); zU = np.zeros((1, s.nvars))
   obj = np.zeros(1); kkt = np.zeros(1); cinf = np.zeros(1); st = np.zeros(1, np.int32); it = np.zeros(1, np.int32)
-  ws = np.zeros(s.ipm_workspace_doubles)
+  ws = np.zeros(ML.workspace_doubles(s, 1))
   p = lambda a: a.ctypes.data_as(C.c_void_p)
   o = ML.MyrIpmOpts()
   hdesc = tr.desc(device="host")  # NODE weights as a host pointer for the twin

@@ -1,0 +1,263 @@
+"""Trajectory-level parity, basin agreement on random start states, solve_with_params.
+
+Every check exists twice: through the HOST TWIN (-m "not gpu": same templates compiled for the CPU, so the algorithm
+is verified in CI without a device) and through the CUDA path (-m gpu: the parity tests proper).
+
+Fixtures (oracle/make_parity.py):
+  tight_<case>.npz    the same NLP solved by SLSQP with ftol=1e-12 (the committed sol_* fixtures stop at SciPy's
+                      default ftol=1e-6, i.e. up to ~3e-5 short of the optimum on flat objectives: VERDICT r1 weak #1)
+  random_x0_c2.npz    16 rows of the bench workload (CARTPOLE trapezoid N=100, random x0) solved by SLSQP
+  params_cartpole.npz reference code (under oracle/refshim) with non-default CARTPOLE (g, m1, m2, length)
+Tolerances: controls / states max |u - u_ref| <= 1e-3 * (bound range), objective 1e-6 relative, re-integrated cost of
+the true system 1e-6 relative, terminal defect 1e-6 absolute -- the contract SURVEY.md section 8c(2,3) states.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests.cases import CASES, GOLDEN, load, product_transcription
+
+TIGHT = sorted(f[len("tight_"):-4] for f in os.listdir(GOLDEN) if f.startswith("tight_"))
+# cases whose optimum is a flat valley in u (SIMPLECASE family: objective curvature ~1e-2, so even ftol=1e-12 pins u
+# only to ~1e-5 * range) keep the same tolerance -- it is met -- but are listed to document the reason when it is tight
+HAVE_RANDOM = os.path.exists(os.path.join(GOLDEN, "random_x0_c2.npz"))
+HAVE_PARAMS = os.path.exists(os.path.join(GOLDEN, "params_cartpole.npz"))
+
+
+def _p(a):
+  return a.ctypes.data_as(C.c_void_p)
+
+
+# ----------------------------------------------------------------------------- two back ends with one interface
+class _Host:
+  """host twin through the C ABI"""
+  name = "host"
+
+  def solve(self, tr, z0, lb, ub, max_iter=1000):
+    from myriad_b200 import _lib as ML
+    d = tr.desc(device="host")
+    s = ML.problem_sizes(d)
+    B = z0.shape[0]
+    z0, lb, ub = (np.ascontiguousarray(a, dtype=np.float64) for a in (z0, lb, ub))
+    out = dict(z=np.zeros((B, s.nvars)), lam=np.zeros((B, s.ncon)), zL=np.zeros((B, s.nvars)), zU=np.zeros((B, s.nvars)),
+               obj=np.zeros(B), kkt=np.zeros(B), cinf=np.zeros(B), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32))
+    ws = np.zeros(ML.workspace_doubles(s, B))
+    o = ML.MyrIpmOpts(); o.max_iter = max_iter
+    ML.check(ML.lib().myr_host_ipm_solve(C.byref(d), C.byref(o), B, _p(z0), _p(lb), _p(ub), _p(out["z"]), _p(out["lam"]), _p(out["zL"]),
+                                         _p(out["zU"]), _p(out["obj"]), _p(out["kkt"]), _p(out["cinf"]), _p(out["status"]), _p(out["iters"]),
+                                         _p(ws), ws.size))
+    return out
+
+  def rollout(self, tr, u, x0):
+    from myriad_b200 import _lib as ML
+    d = tr.desc(device="host")
+    s = ML.problem_sizes(d)
+    B = u.shape[0]
+    steps = tr.intervals * tr.cpi
+    u = np.ascontiguousarray(u, dtype=np.float64); x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    xs = np.zeros((B, steps + 1, s.n)); cost = np.zeros(B)
+    ML.check(ML.lib().myr_host_rollout_cost(C.byref(d), B, u.shape[1], _p(u), _p(x0), _p(xs), _p(cost)))
+    return xs, cost
+
+  def eval(self, tr, z):
+    from myriad_b200 import _lib as ML
+    d = tr.desc(device="host")
+    s = ML.problem_sizes(d)
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    B = z.shape[0]
+    f = np.zeros(B); c = np.zeros((B, s.ncon))
+    ML.check(ML.lib().myr_host_eval(C.byref(d), B, _p(z), None, _p(f), None, _p(c), None, None))
+    return f, c
+
+
+class _Cuda:
+  """CUDA kernels through the C ABI (torch tensors are the device buffers)"""
+  name = "cuda"
+
+  def _dev(self, a):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda().contiguous()
+
+  def solve(self, tr, z0, lb, ub, max_iter=1000):
+    import torch
+    from myriad_b200.engine import Engine
+    out = Engine(tr.desc()).ipm_solve(self._dev(z0), self._dev(lb), self._dev(ub), max_iter=max_iter)
+    torch.cuda.synchronize()
+    r = {k: v.cpu().numpy() for k, v in out.items()}
+    r["cinf"] = r["con_inf"]; r["kkt"] = r["kkt_err"]
+    return r
+
+  def rollout(self, tr, u, x0):
+    import torch
+    from myriad_b200.engine import Engine
+    xs, cost = Engine(tr.desc()).rollout_cost(self._dev(u), self._dev(x0))
+    torch.cuda.synchronize()
+    return xs.cpu().numpy(), cost.cpu().numpy()
+
+  def eval(self, tr, z):
+    import torch
+    from myriad_b200.engine import Engine
+    r = Engine(tr.desc()).eval(self._dev(z))
+    torch.cuda.synchronize()
+    return r.f.cpu().numpy(), r.c.cpu().numpy()
+
+
+BACKENDS = [pytest.param(_Host(), id="host"), pytest.param(_Cuda(), id="cuda", marks=pytest.mark.gpu)]
+
+
+def _ranges(tr, bounds, x_ref, u_ref):
+  """normalisation of trajectory differences: the bound range where finite, else the range of the reference trajectory"""
+  n, m = tr.n, tr.m
+  sb = np.asarray(tr.system.bounds, dtype=np.float64)
+  xr = np.where(np.isfinite(sb[:n, 1] - sb[:n, 0]), sb[:n, 1] - sb[:n, 0], np.maximum(1.0, np.ptp(x_ref, axis=0)))
+  ur = np.where(np.isfinite(sb[n:, 1] - sb[n:, 0]), sb[n:, 1] - sb[n:, 0], np.maximum(1.0, np.ptp(u_ref, axis=0)))
+  return xr, ur
+
+
+# ----------------------------------------------------------------------------- (a) trajectories, rollout cost, defect
+@pytest.mark.parametrize("be", BACKENDS)
+@pytest.mark.parametrize("case", TIGHT)
+def test_trajectories_match_tight_oracle_solve(be, case):
+  fx = load(case)
+  tg = load("tight_" + case)
+  if not bool(tg["success"]):
+    pytest.skip("oracle SLSQP did not converge at ftol=1e-12 for this case")
+  tr = product_transcription(case)
+  out = be.solve(tr, fx["guess"][None], fx["bounds"][None, :, 0], fx["bounds"][None, :, 1])
+  assert int(out["status"][0]) == 0 and float(out["cinf"][0]) <= 1e-8
+  ref = float(tg["cost"])
+  assert abs(float(out["obj"][0]) - ref) <= 1e-6 * max(1.0, abs(ref)), (float(out["obj"][0]), ref)
+  x, u = tr.unravel(out["z"][0])
+  xr, ur = _ranges(tr, fx["bounds"], tg["x"], tg["u"])
+  du = np.abs(u - tg["u"]).max(axis=0) / ur
+  dx = np.abs(x - tg["x"]).max(axis=0) / xr
+  assert du.max() <= 1e-3, ("controls", du)
+  assert dx.max() <= 1e-3, ("states", dx)
+  # what run_trajectory_opt returns (useful_scripts.py:47-49,76): cost and defect of the TRUE system under the solved controls
+  if "rollout_cost" in tg:
+    true_tr = tr
+    if CASES[case][0].startswith("NODE_"):
+      from myriad_b200 import problems as PR
+      true_tr = PR.Transcription(tr.system.true_system, tr.optimizer, tr.method, tr.intervals, tr.cpi)
+    xs, cost = be.rollout(true_tr, u[None], np.asarray(true_tr.system.x_0, dtype=np.float64)[None])
+    rc = float(tg["rollout_cost"])
+    assert abs(float(cost[0]) - rc) <= 1e-6 * max(1.0, abs(rc)), (float(cost[0]), rc)
+    if "rollout_defect" in tg:
+      xT = true_tr.system.x_T
+      idx = [i for i in range(len(xT)) if xT[i] is not None]
+      defect = xs[0, -1, idx] - np.array([xT[i] for i in idx], dtype=np.float64)
+      # the defect of the re-integrated trajectory is sensitive to u: d defect / d u ~ O(T); both sides carry the
+      # solver tolerance of their own u, hence 1e-6 absolute on top of a relative part
+      np.testing.assert_allclose(defect, tg["rollout_defect"], atol=1e-6 + 1e-5 * np.abs(tg["rollout_defect"]).max())
+
+
+# ----------------------------------------------------------------------------- (b) random start states: same basin
+@pytest.mark.skipif(not HAVE_RANDOM, reason="random_x0_c2.npz not generated")
+@pytest.mark.parametrize("be", BACKENDS)
+def test_random_start_states_reach_the_oracle_basin(be):
+  """CARTPOLE swing-up is non-convex: rows of the bench workload must end in the same local solution SLSQP finds
+  (SURVEY.md section 7.4-1).  Agreement is asserted on >= 15 of 16 rows; a row that differs must still be a KKT point
+  with an objective not worse than SLSQP's by more than 1e-6 (a different but better basin is not an error)."""
+  from myriad_b200 import problems as PR
+  rx = dict(np.load(os.path.join(GOLDEN, "random_x0_c2.npz")))
+  tr = product_transcription("c2_cartpole_trap_100")
+  import torch
+  x0 = torch.as_tensor(rx["x0"])
+  if be.name == "cuda":
+    z0, lb, ub = (t.cpu().numpy() for t in PR.build_batch(tr, x0.cuda()))
+  else:
+    pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+      # build_batch needs the device only for rolled-out guesses; CARTPOLE's guess is a linspace: build it in numpy
+      fx = load("c2_cartpole_trap_100")
+      B = x0.shape[0]
+      z0 = np.tile(fx["guess"], (B, 1)); lb = np.tile(fx["bounds"][:, 0], (B, 1)); ub = np.tile(fx["bounds"][:, 1], (B, 1))
+      n, L = tr.n, tr.nx_nodes
+      xT = np.asarray(tr.system.x_T, dtype=np.float64)
+      k = np.arange(L, dtype=np.float64)
+      for b in range(B):
+        a = rx["x0"][b]
+        xg = a[None, :] + k[:, None] * ((xT - a) / (L - 1))[None, :]
+        xg[-1] = xT
+        z0[b, :L * n] = xg.reshape(-1)
+        lb[b, :n] = a; ub[b, :n] = a
+    else:
+      z0, lb, ub = (t.cpu().numpy() for t in PR.build_batch(tr, x0.cuda()))
+  out = be.solve(tr, z0, lb, ub)
+  ok = out["status"] == 0
+  assert ok.sum() >= 15, out["status"]
+  same = np.abs(out["obj"] - rx["cost_tight"]) <= 1e-6 * np.maximum(1.0, np.abs(rx["cost_tight"]))
+  assert (same & ok).sum() >= 15, (out["obj"], rx["cost_tight"])
+  better = out["obj"] <= rx["cost_tight"] + 1e-6 * np.maximum(1.0, np.abs(rx["cost_tight"]))
+  assert (ok & (same | better)).sum() >= 15
+  # trajectories of the rows in the same basin
+  x, u = tr.unravel(out["z"])
+  sel = same & ok & rx["success"]
+  assert np.abs(u[sel] - rx["u_tight"][sel]).max() <= 1e-3 * 40.0      # u range of CARTPOLE = [-20, 20]
+  # row 0 is the reference problem itself
+  fx = load("c2_cartpole_trap_100")
+  assert abs(out["obj"][0] - float(fx["sol_cost"])) <= 5e-5 * abs(float(fx["sol_cost"]))
+
+
+# ----------------------------------------------------------------------------- (c) solve_with_params
+def _param_system():
+  from myriad_b200.systems import SystemType
+  pf = dict(np.load(os.path.join(GOLDEN, "params_cartpole.npz")))
+  g, m1, m2, length = (float(v) for v in pf["params"])
+  return pf, SystemType.CARTPOLE(g=g, m1=m1, m2=m2, length=length), dict(g=g, m1=m1, m2=m2, length=length)
+
+
+@pytest.mark.skipif(not HAVE_PARAMS, reason="params_cartpole.npz not generated")
+@pytest.mark.parametrize("be", BACKENDS)
+def test_parametrized_system_matches_reference(be):
+  """Non-default CARTPOLE (g, m1, m2, length): K1 values at a test point and the solved objective against the
+  reference's parametrized_objective / parametrized_constraints / solve_with_params (shooting: base.py:81-93) and
+  against the optimizer of hp.system(**params) (trapezoid: the evident intent)."""
+  from myriad_b200 import problems as PR
+  pf, system, _ = _param_system()
+  for key, tr in (("shoot", PR.Transcription(system, PR.SHOOTING, "HEUN", 5, 4)),
+                  ("trap", PR.Transcription(system, PR.TRAPEZOIDAL, "HEUN", 10, 1))):
+    f, c = be.eval(tr, pf[key + "_z"][None])
+    np.testing.assert_allclose(f[0], float(pf[key + "_obj_z"]), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(c[0], pf[key + "_con_z"], rtol=1e-12, atol=1e-13)
+    base = product_transcription("s_cartpole_shooting_5x4_heun" if key == "shoot" else "s_cartpole_trap_10")
+    fx = load("s_cartpole_shooting_5x4_heun" if key == "shoot" else "s_cartpole_trap_10")
+    # the reference keeps self.guess / self.bounds of the default system (base.py:84-87)
+    out = be.solve(tr, fx["guess"][None], fx["bounds"][None, :, 0], fx["bounds"][None, :, 1])
+    assert int(out["status"][0]) == 0 and float(out["cinf"][0]) <= 1e-8
+    ref = float(pf[key + "_sol_cost"])
+    assert abs(float(out["obj"][0]) - ref) <= 5e-5 * abs(ref), (key, float(out["obj"][0]), ref)
+    # and the parameters matter: the default system gives a different optimum
+    out0 = be.solve(base, fx["guess"][None], fx["bounds"][None, :, 0], fx["bounds"][None, :, 1])
+    assert abs(float(out0["obj"][0]) - ref) > 1e-2 * abs(ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not HAVE_PARAMS, reason="params_cartpole.npz not generated")
+def test_solve_with_params_surface():
+  """TrajectoryOptimizer.solve_with_params (base.py:81-93) through the mirrored surface, CUDA path."""
+  from myriad_b200.config import Config, HParams, IntegrationMethod, OptimizerType
+  from myriad_b200.systems import SystemType
+  from myriad_b200.trajectory_optimizers import get_optimizer
+  pf, _, params = _param_system()
+  cfg = Config(verbose=False, plot=False)
+  hp = HParams(system=SystemType.CARTPOLE, optimizer=OptimizerType.SHOOTING, integration_method=IntegrationMethod.HEUN,
+               intervals=5, controls_per_interval=4)
+  opt = get_optimizer(hp, cfg, hp.system())
+  np.testing.assert_allclose(opt.parametrized_objective(params, pf["shoot_z"]), float(pf["shoot_obj_z"]), rtol=1e-12, atol=1e-14)
+  np.testing.assert_allclose(opt.parametrized_constraints(params, pf["shoot_z"]), pf["shoot_con_z"], rtol=1e-12, atol=1e-13)
+  res = opt.solve_with_params(params)
+  assert abs(res["cost"] - float(pf["shoot_sol_cost"])) <= 5e-5 * abs(float(pf["shoot_sol_cost"]))
+  assert set(("x", "u", "xs_and_us", "cost", "lambda")) <= set(res)
+  hp2 = HParams(system=SystemType.CARTPOLE, optimizer=OptimizerType.COLLOCATION, intervals=10)
+  opt2 = get_optimizer(hp2, cfg, hp2.system())
+  res2 = opt2.solve_with_params(params)
+  assert abs(res2["cost"] - float(pf["trap_sol_cost"])) <= 5e-5 * abs(float(pf["trap_sol_cost"]))
+  # many calls must not grow the engine cache (unbounded _ENGINES)
+  from myriad_b200 import nlp_solvers
+  n0 = len(nlp_solvers._ENGINES)
+  for k in range(3):
+    opt2.solve_with_params({**params, "g": 9.0 + 0.1 * k})
+  assert len(nlp_solvers._ENGINES) <= max(n0 + 3, nlp_solvers.MAX_ENGINES)
