@@ -59,6 +59,9 @@ enum {
   MYR_SYS_TUMOUR = 14,
   MYR_SYS_PREDATORPREY = 15,
   MYR_SYS_BEARPOPULATIONS = 16,
+  MYR_SYS_ROCKETLANDING = 17,
+  MYR_SYS_PENDULUM = 18,     /* non-smooth: clip / angle_normalize with JAX's sub-gradient choices */
+  MYR_SYS_MOUNTAINCAR = 19,  /* non-smooth: clipped force */
   /* NodeSystem (myriad/systems/neural_ode/node_system.py:14-42) wrapping true system k: id = MYR_SYS_NODE_BASE + k.
    * Dynamics = the NODE MLP of myriad/neural_ode/create_node.py:110-117 (weights in MyrDesc.theta); cost, bounds,
    * horizon and the verification rollout are the true system's. */
@@ -179,6 +182,18 @@ int myr_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B,
 int myr_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double* u, const double* x0,
                      double* xs, double* cost, void* stream);
 
+/* Point evaluation of a system for B (x, u, t) points in one launch: f = dynamics(x, u, t) and g = cost(x, u, t).
+ * Replaces FiniteHorizonControlSystem.dynamics / .cost (myriad/systems/base.py:45-73) when host code calls them
+ * (the solver itself evaluates them inside K1).  x: [B][n]; u: [B][m]; t: [B] or NULL (0); f: [B][n] or NULL; g: [B] or NULL.
+ * NODE systems evaluate the MLP dynamics (node_system.py:36-38) and the true system's cost. */
+int myr_dynamics(const MyrDesc* desc, int B, const double* x, const double* u, const double* t,
+                 double* f, double* g, void* stream);
+
+/* out[b] = J(z_b)^T lam[b] ([B][nvars], reference layout) from the compact block Jacobian Jblk that myr_eval returned:
+ * the vector-Jacobian product the reference takes with jax.grad of the Lagrangian in its extragradient solver
+ * (myriad/nlp_solvers/extra_gradient.py:21-33).  Works for all three transcriptions. */
+int myr_jtvec(const MyrDesc* desc, int B, const double* Jblk, const double* lam, double* out, void* stream);
+
 /* Measurement helper (no reference counterpart): launches `blocks` CTAs x 1024 threads, each doing `iters` rounds of 8
  * independent fp64 FMAs (2 * 8 * iters * 1024 * blocks flops); out: [blocks * 1024] doubles.  bench.py times it with
  * CUDA events to get the device's fp64 FMA peak, the denominator for the KKT / interior-point kernel's FLOP/s. */
@@ -198,6 +213,9 @@ int myr_host_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B,
                        double* ws, size_t ws_doubles);
 int myr_host_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double* u, const double* x0,
                           double* xs, double* cost);
+int myr_host_dynamics(const MyrDesc* desc, int B, const double* x, const double* u, const double* t,
+                      double* f, double* g);
+int myr_host_jtvec(const MyrDesc* desc, int B, const double* Jblk, const double* lam, double* out);
 
 #ifdef __cplusplus
 }

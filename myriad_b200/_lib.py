@@ -20,6 +20,7 @@ NODE_BASE = 100
 SYSTEM_IDS = {
   "SIMPLECASE": 0, "CARTPOLE": 1, "VANDERPOL": 2, "CANCERTREATMENT": 3, "MOULDFUNGICIDE": 4, "BIOREACTOR": 5,
   "SIMPLECASEWITHBOUNDS": 6, "GLUCOSE": 7, "HARVEST": 8, "TIMBERHARVEST": 9, "SEIR": 10, "EPIDEMICSEIRN": 11, "HIVTREATMENT": 12, "BACTERIA": 13, "TUMOUR": 14, "PREDATORPREY": 15, "BEARPOPULATIONS": 16,
+  "ROCKETLANDING": 17, "PENDULUM": 18, "MOUNTAINCAR": 19,
 }
 OPT_SHOOTING, OPT_TRAPEZOIDAL, OPT_HERMITE_SIMPSON = 0, 1, 2
 METHOD_IDS = {"EULER": 0, "HEUN": 1, "MIDPOINT": 2, "RK4": 3}
@@ -58,7 +59,8 @@ _P = C.c_void_p
 _lib = None
 
 EXPORTS = ["myr_abi_version", "myr_last_error", "myr_problem_sizes", "myr_eval", "myr_kkt_solve", "myr_ipm_solve",
-           "myr_rollout_cost", "myr_bench_dfma", "myr_host_eval", "myr_host_kkt_solve", "myr_host_ipm_solve", "myr_host_rollout_cost"]
+           "myr_rollout_cost", "myr_dynamics", "myr_jtvec", "myr_bench_dfma", "myr_host_eval", "myr_host_kkt_solve", "myr_host_ipm_solve",
+           "myr_host_rollout_cost", "myr_host_dynamics", "myr_host_jtvec"]
 
 
 def lib() -> C.CDLL:
@@ -84,6 +86,12 @@ def lib() -> C.CDLL:
   ro = [C.POINTER(MyrDesc), C.c_int, C.c_int, _P, _P, _P, _P]
   L.myr_rollout_cost.argtypes = ro + [_P]
   L.myr_host_rollout_cost.argtypes = ro
+  dy = [C.POINTER(MyrDesc), C.c_int, _P, _P, _P, _P, _P]
+  L.myr_dynamics.argtypes = dy + [_P]
+  L.myr_host_dynamics.argtypes = dy
+  jt = [C.POINTER(MyrDesc), C.c_int, _P, _P, _P]
+  L.myr_jtvec.argtypes = jt + [_P]
+  L.myr_host_jtvec.argtypes = jt
   L.myr_bench_dfma.argtypes = [C.c_int, C.c_int, _P, _P]
   for name in EXPORTS:
     if name not in ("myr_abi_version", "myr_last_error"):

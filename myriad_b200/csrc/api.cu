@@ -34,6 +34,9 @@ double system_default_T(int id) {
     case MYR_SYS_TUMOUR: return 1.2;
     case MYR_SYS_PREDATORPREY: return 10.0;
     case MYR_SYS_BEARPOPULATIONS: return 25.0;
+    case MYR_SYS_ROCKETLANDING: return 16.0;
+    case MYR_SYS_PENDULUM: return 15.0;
+    case MYR_SYS_MOUNTAINCAR: return 300.0;
     default: return 1.0;
   }
 }
@@ -126,6 +129,24 @@ extern "C" int myr_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const d
 extern "C" int myr_host_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double* u, const double* x0, double* xs, double* cost) {
   MYR_GET(desc);
   return vt->host_rollout(desc, B, nu_rows, u, x0, xs, cost);
+}
+
+extern "C" int myr_dynamics(const MyrDesc* desc, int B, const double* x, const double* u, const double* t, double* f, double* g, void* stream) {
+  MYR_GET(desc);
+  return vt->dynamics(desc, B, x, u, t, f, g, stream);
+}
+extern "C" int myr_host_dynamics(const MyrDesc* desc, int B, const double* x, const double* u, const double* t, double* f, double* g) {
+  MYR_GET(desc);
+  return vt->host_dynamics(desc, B, x, u, t, f, g);
+}
+
+extern "C" int myr_jtvec(const MyrDesc* desc, int B, const double* Jblk, const double* lam, double* out, void* stream) {
+  MYR_GET(desc);
+  return vt->jtvec(desc, B, Jblk, lam, out, stream);
+}
+extern "C" int myr_host_jtvec(const MyrDesc* desc, int B, const double* Jblk, const double* lam, double* out) {
+  MYR_GET(desc);
+  return vt->host_jtvec(desc, B, Jblk, lam, out);
 }
 
 // ------------------------------------------------------------------ measurement helper

@@ -313,6 +313,8 @@ MYR_HDI bool sym_inverse_inertia_fast(const double* A, uint32_t mask, double* in
 }
 
 // inverse + inertia: fast path first, pivoted fallback
+// The pivoted routine is out of line and takes pointers: it works on ITS OWN copies so that the caller's A / inv never
+// have their address escape and stay in registers on the (overwhelmingly common) fast path.
 template <int N>
 MYR_HDI void sym_inverse(double* A, uint32_t mask, double* inv, int& npos, int& nneg, int& nzero, double* piv_ratio = nullptr) {
   nzero = 0;
@@ -322,7 +324,14 @@ MYR_HDI void sym_inverse(double* A, uint32_t mask, double* inv, int& npos, int& 
     return;
   }
   if (piv_ratio) *piv_ratio = 0.0;  // pivoted fallback: treat as ill-conditioned
-  sym_inverse_inertia<N>(A, mask, inv, npos, nneg, nzero);
+  double A2[N * N], inv2[N * N];
+  int p2_, n2_, z2_;
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) A2[i] = A[i];
+  sym_inverse_inertia<N>(A2, mask, inv2, p2_, n2_, z2_);
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) inv[i] = inv2[i];
+  npos = p2_; nneg = n2_; nzero = z2_;
 }
 
 }  // namespace myr

@@ -432,7 +432,9 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
         for (int r = 0; r < NC; ++r)
 #pragma unroll
           for (int c = 0; c < NC; ++c) A[r * NC + c] = 0.5 * (Di[r * NC + c] + Di[c * NC + r]);
-        sym_inverse_inertia<NC>(A, 0u, inv, p_, n_, z_);
+        int p2_, n2_, z2_;
+        sym_inverse_inertia<NC>(A, 0u, inv, p2_, n2_, z2_);
+        p_ = p2_; n_ = n2_; z_ = z2_;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           double v = 0.0;
@@ -1008,7 +1010,7 @@ MYR_HDI bool kkt_solve(const Problem& P, const WS<S>& ws, double delta_w, double
 // Second-order-correction solve (IPOPT A-5.5 ff.) with the factors the last kkt_solve left behind: same matrix,
 // constraint right-hand side csoc instead of c.   S dl2 = csoc - J Hinv rb,   dz2 = -Hinv (rb + J^T dl2).
 template <class S>
-MYR_HDN void kkt_soc_solve(const Problem& P, const WS<S>& ws) {
+MYR_HDI void kkt_soc_solve(const Problem& P, const WS<S>& ws) {
   constexpr int NC = S::NC;
   for (int k = MYR_TID; k < ws.St * NC; k += MYR_NT) ws.crb[k] = ws.csoc[k] + ws.sch[k];
   MYR_SYNC();

@@ -792,6 +792,162 @@ int sys_host_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double*
   return (int)MYR_OK;
 }
 
+// ------------------------------------------------------------------ VJP with the compact block Jacobian
+// out = J^T lam in the reference's flat layout, from the Jblk that myr_eval returned.  This is the product the
+// reference's extragradient solver takes through jax.grad of the Lagrangian (nlp_solvers/extra_gradient.py:21-33).
+template <class S>
+MYR_HDI void jtvec_node(const Problem& P, int b, int q, int Q, int St, const double* Jblk, const double* lam, double* out) {
+  constexpr int NW = S::NW, NC = S::NC;
+  const long long jstride = (long long)St * S::kMaxStageNodes * NC * NW;
+  const double* Jb = Jblk + (long long)b * jstride;
+  const double* lb = lam + (long long)b * P.ncon;
+  double acc[NW];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) acc[i] = 0.0;
+  const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
+  if (jp >= 0) {
+    const double* G = Jb + ((long long)jp * S::kMaxStageNodes + S::phi_slot(P, q)) * NC * NW;
+#pragma unroll
+    for (int r = 0; r < NC; ++r) {
+      const double l = lb[S::cidx(P, jp, r)];
+#pragma unroll
+      for (int i = 0; i < NW; ++i) acc[i] += G[r * NW + i] * l;
+    }
+  }
+  if (js >= 0) {
+    const double* F = Jb + ((long long)js * S::kMaxStageNodes + S::psi_slot(P, q)) * NC * NW;
+#pragma unroll
+    for (int r = 0; r < NC; ++r) {
+      const double l = lb[S::cidx(P, js, r)];
+#pragma unroll
+      for (int i = 0; i < NW; ++i) acc[i] += F[r * NW + i] * l;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NW; ++i) out[(long long)b * P.nvars + S::zidx(P, q, i)] = acc[i];
+}
+
+template <class S>
+__global__ void jtvec_kernel(Problem P, int Q, int St, const double* Jblk, const double* lam, double* out) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id < (long long)P.B * Q) jtvec_node<S>(P, (int)(id / Q), (int)(id % Q), Q, St, Jblk, lam, out);
+}
+
+// shooting: Jblk[b][k] is (n+1) x ncol (rows 0..n-1: d px_k / d (xs[k], controls of interval k)); c_k = px_k - xs[k+1].
+// One thread per OUTPUT variable gathers from the (at most two) intervals that touch it: no atomics, deterministic.
+template <class Sys, int NU>
+MYR_HDI void jtvec_shooting_var(const Problem& P, int b, int v, const double* Jblk, const double* lam, double* out) {
+  constexpr int n = Sys::n, m = Sys::m;
+  constexpr int mc = NU == 3 ? 2 : 1;
+  const int M = mc * P.cpi, ncol = n + (M + 1) * m, K = P.N;
+  const double* lb = lam + (long long)b * P.ncon;
+  const double* Jb = Jblk + (long long)b * K * (n + 1) * ncol;
+  double a = 0.0;
+  const int nx = (K + 1) * n;
+  if (v < nx) {
+    const int k = v / n, i = v % n;
+    if (k < K) for (int r = 0; r < n; ++r) a += Jb[((long long)k * (n + 1) + r) * ncol + i] * lb[k * n + r];
+    if (k >= 1) a -= lb[(k - 1) * n + i];
+  } else {
+    const int uidx = (v - nx) / m, c = (v - nx) % m;   // control row uidx, component c
+    for (int k = max(0, (uidx - 1) / M - 1); k < K && k * M <= uidx; ++k) {
+      const int loc = uidx - k * M;
+      if (loc < 0 || loc > M) continue;
+      for (int r = 0; r < n; ++r) a += Jb[((long long)k * (n + 1) + r) * ncol + n + loc * m + c] * lb[k * n + r];
+    }
+  }
+  out[(long long)b * P.nvars + v] = a;
+}
+
+template <class Sys, int NU>
+__global__ void jtvec_shooting_kernel(Problem P, const double* Jblk, const double* lam, double* out) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id < (long long)P.B * P.nvars) jtvec_shooting_var<Sys, NU>(P, (int)(id / P.nvars), (int)(id % P.nvars), Jblk, lam, out);
+}
+
+template <class Sys>
+int sys_jtvec(const MyrDesc* desc, int B, const double* Jblk, const double* lam, double* out, void* stream, int host) {
+  if (B > 0 && (!Jblk || !lam || !out)) return fail(MYR_E_BADARG, "null buffer passed to myr_jtvec%s", "");
+  if (desc->optimizer == MYR_OPT_SHOOTING) {
+    return dispatch_shooting<Sys>(desc, B, [&](auto s, const Problem& P) {
+      using S = decltype(s);
+      constexpr int NU = (S::NW - S::n) / S::m;
+      if (B == 0) return (int)MYR_OK;
+      const long long tot = (long long)B * P.nvars;
+      if (host) {
+        for (long long id = 0; id < tot; ++id) jtvec_shooting_var<Sys, NU>(P, (int)(id / P.nvars), (int)(id % P.nvars), Jblk, lam, out);
+        return (int)MYR_OK;
+      }
+      jtvec_shooting_kernel<Sys, NU><<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P, Jblk, lam, out);
+      return cuda_check("myr_jtvec(shooting)");
+    });
+  }
+  return dispatch_scheme<Sys>(desc, B, [&](auto s, const Problem& P) {
+    using S = decltype(s);
+    if (B == 0) return (int)MYR_OK;
+    const int Q = S::num_nodes(P), St = S::num_stages(P);
+    const long long tot = (long long)B * Q;
+    if (host) {
+      for (long long id = 0; id < tot; ++id) jtvec_node<S>(P, (int)(id / Q), (int)(id % Q), Q, St, Jblk, lam, out);
+      return (int)MYR_OK;
+    }
+    jtvec_kernel<S><<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P, Q, St, Jblk, lam, out);
+    return cuda_check("myr_jtvec");
+  });
+}
+template <class Sys>
+int sys_jtvec_dev(const MyrDesc* desc, int B, const double* Jblk, const double* lam, double* out, void* stream) {
+  return sys_jtvec<Sys>(desc, B, Jblk, lam, out, stream, 0);
+}
+template <class Sys>
+int sys_jtvec_host(const MyrDesc* desc, int B, const double* Jblk, const double* lam, double* out) {
+  return sys_jtvec<Sys>(desc, B, Jblk, lam, out, nullptr, 1);
+}
+
+// ------------------------------------------------------------------ point evaluation of a system (systems/base.py:45-73)
+template <class Sys>
+MYR_HDI void dynamics_point(const Problem& P, int b, const double* x, const double* u, const double* t, double* f, double* g) {
+  constexpr int n = Sys::n, m = Sys::m;
+  double xv[n], uv[m], fv[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) xv[i] = x[(long long)b * n + i];
+#pragma unroll
+  for (int i = 0; i < m; ++i) uv[i] = u[(long long)b * m + i];
+  if (f) {
+    dyn_f<Sys>(P, xv, uv, fv);
+#pragma unroll
+    for (int i = 0; i < n; ++i) f[(long long)b * n + i] = fv[i];
+  }
+  if (g) g[b] = Sys::cost(xv, uv, t ? t[b] : 0.0, P.p);
+}
+
+template <class Sys>
+__global__ void dynamics_kernel(Problem P, const double* x, const double* u, const double* t, double* f, double* g) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < P.B) dynamics_point<Sys>(P, b, x, u, t, f, g);
+}
+
+template <class Sys>
+int sys_dynamics(const MyrDesc* desc, int B, const double* x, const double* u, const double* t, double* f, double* g, void* stream) {
+  Problem P;
+  int rc = make_problem<Sys>(desc, B, P);
+  if (rc) return rc;
+  if (B == 0) return (int)MYR_OK;
+  if (!x || !u) return fail(MYR_E_BADARG, "x / u is null%s", "");
+  dynamics_kernel<Sys><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, x, u, t, f, g);
+  return cuda_check("myr_dynamics");
+}
+
+template <class Sys>
+int sys_host_dynamics(const MyrDesc* desc, int B, const double* x, const double* u, const double* t, double* f, double* g) {
+  Problem P;
+  int rc = make_problem<Sys>(desc, B, P);
+  if (rc) return rc;
+  if (B > 0 && (!x || !u)) return fail(MYR_E_BADARG, "x / u is null%s", "");
+  for (int b = 0; b < B; ++b) dynamics_point<Sys>(P, b, x, u, t, f, g);
+  return (int)MYR_OK;
+}
+
 // the verification rollout of a NodeSystem integrates the TRUE dynamics (node_system.py:32-33, useful_scripts.py:47-49)
 template <class Sys, class = void>
 struct rollout_system { using type = Sys; };
@@ -803,7 +959,7 @@ SysVTable make_vtable() {
   using R = typename rollout_system<Sys>::type;
   return SysVTable{Sys::id, Sys::name, &sys_problem_sizes<Sys>, &sys_eval<Sys>, &sys_host_eval<Sys>, &sys_kkt_solve<Sys>,
                    &sys_host_kkt_solve<Sys>, &sys_ipm_solve<Sys>, &sys_host_ipm_solve<Sys>, &sys_rollout_cost<R>,
-                   &sys_host_rollout_cost<R>};
+                   &sys_host_rollout_cost<R>, &sys_dynamics<Sys>, &sys_host_dynamics<Sys>, &sys_jtvec_dev<Sys>, &sys_jtvec_host<Sys>};
 }
 
 }  // namespace myr

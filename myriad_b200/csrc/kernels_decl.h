@@ -22,5 +22,9 @@ struct SysVTable {
                   double*, double*, double*, int32_t*, int32_t*, double*, size_t);
   int (*rollout)(const MyrDesc*, int, int, const double*, const double*, double*, double*, void*);
   int (*host_rollout)(const MyrDesc*, int, int, const double*, const double*, double*, double*);
+  int (*dynamics)(const MyrDesc*, int, const double*, const double*, const double*, double*, double*, void*);
+  int (*host_dynamics)(const MyrDesc*, int, const double*, const double*, const double*, double*, double*);
+  int (*jtvec)(const MyrDesc*, int, const double*, const double*, double*, void*);
+  int (*host_jtvec)(const MyrDesc*, int, const double*, const double*, double*);
 };
 }  // namespace myr

@@ -73,6 +73,15 @@ class Engine:
                                _ptr(out.Jblk), _ptr(out.Hblk) if hessian else None, _stream()))
     return out
 
+  def jtvec(self, Jblk: torch.Tensor, lam: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """J^T lam ([B, nvars], reference layout) from the compact block Jacobian of ``eval`` (myr_jtvec)"""
+    _need_cuda(Jblk, lam)
+    B = lam.shape[0]
+    if out is None:
+      out = torch.empty(B, self.sizes.nvars, dtype=torch.float64, device=lam.device)
+    ML.check(ML.lib().myr_jtvec(C.byref(self.desc), B, _ptr(Jblk), _ptr(lam), _ptr(out), _stream()))
+    return out
+
   def workspace(self, B: int, device) -> torch.Tensor:
     need = ML.workspace_doubles(self.sizes, B)
     if self._ws is None or self._ws.numel() < need or self._ws.device != device:

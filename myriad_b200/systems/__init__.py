@@ -176,6 +176,47 @@ class BearPopulations(FiniteHorizonControlSystem):
                      device_name="BEARPOPULATIONS", params=[r, K, m_p, m_f, c_p, c_f])
 
 
+class RocketLanding(FiniteHorizonControlSystem):
+  """myriad/systems/miscellaneous/rocket_landing.py:54-124 (six states, two controls)"""
+
+  def __init__(self, g: float = 9.8, m: float = 100_000, length: float = 50, width: float = 10) -> None:
+    self.g, self.m, self.length, self.width = g, m, length, width
+    self.min_thrust, self.max_thrust = 880 * 1000, 1 * 2210 * 1000
+    self.I = 1 / 12 * m * length ** 2
+    deg_to_rad = 0.01745329
+    self.max_gimble = 20 * deg_to_rad
+    self.min_gimble = -self.max_gimble
+    self.min_percent_thrust, self.max_percent_thrust = 0.4, 1.
+    super().__init__(x_0=np.array([0., 0., 1000., -80., -np.pi / 2., 0.]), x_T=np.array([0., 0., 0., 0., 0., 0.]), T=16.,
+                     bounds=np.array([[-250., 150.], [-250., 150.], [0., 1000.], [-250., 150.], [-2 * np.pi, 2 * np.pi],
+                                      [-250., 150.], [self.min_percent_thrust, self.max_percent_thrust],
+                                      [self.min_gimble, self.max_gimble]]),
+                     terminal_cost=False, device_name="ROCKETLANDING", params=[g, m, length, self.max_thrust])
+
+
+class Pendulum(FiniteHorizonControlSystem):
+  """myriad/systems/classical_control/pendulum.py:50-119.  Non-smooth (clipped torque and speed, normalised angle):
+  the generated device code takes JAX's derivative choices (clip: 1 strictly inside, 0 outside; remainder: 1)."""
+
+  def __init__(self, g: float = 10., m: float = 1., length: float = 1.):
+    self.g, self.m, self.length = g, m, length
+    self.max_speed, self.max_torque, self.ctrl_penalty = 8., 2., 0.001
+    super().__init__(x_0=np.array([0., 0.]), x_T=np.array([np.pi, 0.]), T=15,
+                     bounds=np.array([[-np.pi, np.pi], [-self.max_speed, self.max_speed], [-self.max_torque, self.max_torque]]),
+                     terminal_cost=False, device_name="PENDULUM",
+                     params=[g, m, length, self.max_speed, self.max_torque, self.ctrl_penalty])
+
+
+class MountainCar(FiniteHorizonControlSystem):
+  """myriad/systems/classical_control/mountain_car.py:53-107 (hill_function(x) = x^2 / 2, :11-13; clipped force)"""
+
+  def __init__(self, power=0.0015, gravity=0.0025) -> None:
+    self.power, self.gravity = power, gravity
+    super().__init__(x_0=np.array([-0.1, 0.]), x_T=np.array([0.45, 0.]), T=300.,
+                     bounds=np.array([[-1.2, 0.6], [-0.07, 0.07], [-1.0, 1.0]]), terminal_cost=False,
+                     device_name="MOUNTAINCAR", params=[power, gravity])
+
+
 class NodeSystem(FiniteHorizonControlSystem):
   """myriad/systems/neural_ode/node_system.py:14-42: a system whose (parametrized) dynamics is the neural-ODE MLP of
   myriad/neural_ode/create_node.py:110-117 applied to concat(x, u), while cost, bounds, horizon, start/end states and
@@ -247,8 +288,8 @@ class SystemType(Enum):
   VANDERPOL = VanDerPol
   SEIR = SEIR
   TUMOUR = Tumour
-  MOUNTAINCAR = _NotOnDevice("MOUNTAINCAR")
-  PENDULUM = _NotOnDevice("PENDULUM")
+  MOUNTAINCAR = MountainCar
+  PENDULUM = Pendulum
   SIMPLECASE = SimpleCase
   MOULDFUNGICIDE = MouldFungicide
   BACTERIA = Bacteria
@@ -263,7 +304,7 @@ class SystemType(Enum):
   BIOREACTOR = Bioreactor
   PREDATORPREY = PredatorPrey
   INVASIVEPLANT = _NotOnDevice("INVASIVEPLANT")
-  ROCKETLANDING = _NotOnDevice("ROCKETLANDING")
+  ROCKETLANDING = RocketLanding
 
   def __call__(self, *args, **kwargs) -> FiniteHorizonControlSystem:
     return self.value(*args, **kwargs)

@@ -94,7 +94,9 @@ class TrajectoryOptimizer(object):
   def solve_with_params(self, params, guess: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
     """base.py:81-93: plan with a system built from ``params`` (hp.system(**params), useful_scripts.py:35)."""
     other = self._with_params(params)
-    inputs = other._opt_inputs()
+    # like the reference, the guess and the bounds stay those of THIS optimizer; only the dynamics / cost change
+    inputs = {**self._opt_inputs(), 'objective': other.objective, 'constraints': other.constraints,
+              'transcription': other.transcription}
     if guess is not None:
       inputs['guess'] = guess
     from myriad_b200.nlp_solvers import solve

@@ -44,3 +44,51 @@ def get_defect(system, learned_xs) -> Optional[np.ndarray]:
   if defect is not None:
     defect = np.array(defect)
   return defect
+
+
+def generate_dataset(hp: HParams, cfg, given_us=None, seed: Optional[int] = None) -> np.ndarray:
+  """Mirror of myriad/utils.py:327-444: ``train_size + val_size + test_size`` random control trajectories and the state
+  trajectories the TRUE system follows under them -- every rollout of the dataset in ONE launch of the CUDA rollout
+  kernel (the reference vmaps integrate_time_independent over the trajectories, :422-424).
+
+  Control sampling follows the reference draw for draw where it uses NumPy's global generator (RANDOM_WALK, :349-358:
+  seed it with np.random.seed(hp.seed) as useful_scripts.py does); where the reference draws from jax.random (UNIFORM,
+  TRUE_OPTIMAL / CURRENT_OPTIMAL, start-state spread, observation noise) a torch CPU generator seeded with ``seed``
+  (default hp.seed) is used instead -- JAX's PRNG stream is not reproducible without jax.
+  Returns xs_and_us [total, num_steps + 1, n + m] as a NumPy array."""
+  from myriad_b200.config import SamplingApproach
+  system = hp.system()
+  total = hp.train_size + hp.val_size + hp.test_size
+  n, m = hp.state_size, hp.control_size
+  b = np.asarray(system.bounds, dtype=np.float64)
+  x_lower, x_upper, u_lower, u_upper = b[:n, 0], b[:n, 1], b[n:, 0], b[n:, 1]
+  if np.isinf(u_lower).any() or np.isinf(u_upper).any():
+    raise Exception("infinite control bounds, aborting")
+  if np.isinf(x_lower).any() or np.isinf(x_upper).any():
+    raise Exception("infinite state bounds, aborting")
+  gen = torch.Generator(device="cpu").manual_seed(int(hp.seed if seed is None else seed))
+  spread = (u_upper - u_lower) * hp.sample_spread
+  if hp.sampling_approach == SamplingApproach.RANDOM_WALK:
+    all_us = np.random.uniform(u_lower, u_upper, (total, 1, m))
+    for _ in range(hp.num_steps):
+      next_us = np.random.normal(0, spread, (total, 1, m))
+      all_us = np.concatenate((all_us, np.clip(next_us + all_us[:, -1:, :], u_lower, u_upper)), axis=1)
+  elif hp.sampling_approach == SamplingApproach.UNIFORM or given_us is None:
+    r = torch.rand(total, hp.num_steps + 1, m, generator=gen, dtype=torch.float64).numpy()
+    all_us = (u_lower + r * (u_upper - u_lower)) * 0.75
+  elif hp.sampling_approach in (SamplingApproach.TRUE_OPTIMAL, SamplingApproach.CURRENT_OPTIMAL):
+    noise = torch.randn(total, hp.num_steps + 1, m, generator=gen, dtype=torch.float64).numpy() * (u_upper - u_lower) * hp.sample_spread
+    all_us = np.clip(np.asarray(given_us, dtype=np.float64).reshape(1, hp.num_steps + 1, m) + noise, u_lower, u_upper)
+  else:
+    raise Exception("Unknown sampling approach, please choose among", [s.name for s in SamplingApproach])
+  start = np.repeat(np.asarray(system.x_0, dtype=np.float64)[None], total, axis=0)
+  if hp.start_spread > 0.:
+    start = np.clip(start + torch.randn(total, n, generator=gen, dtype=torch.float64).numpy() * hp.start_spread, x_lower, x_upper)
+  xs, _ = get_state_trajectory_and_cost_batch(hp, system, torch.as_tensor(start).cuda(), torch.as_tensor(all_us).cuda())
+  all_xs = xs.cpu().numpy()
+  if hp.noise_level > 0.:
+    all_xs = all_xs + torch.randn(all_xs.shape, generator=gen, dtype=torch.float64).numpy() * (x_upper - x_lower) * hp.noise_level
+  all_xs = np.clip(all_xs, x_lower, x_upper)
+  out = np.concatenate((all_xs, all_us), axis=2)
+  assert np.isfinite(out).all()
+  return out

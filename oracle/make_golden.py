@@ -76,6 +76,15 @@ CASES = {
   "x_bear_hs_6": ("BEARPOPULATIONS", "COLLOCATION", "HERMITE_SIMPSON", "RK4", 6, 1),
   "x_bear_shooting_3x4_heun": ("BEARPOPULATIONS", "SHOOTING", "TRAPEZOIDAL", "HEUN", 3, 4),
   "x_bear_shooting_2x3_rk4": ("BEARPOPULATIONS", "SHOOTING", "TRAPEZOIDAL", "RK4", 2, 3),
+  # round 2: the remaining continuous SystemType members -- ROCKETLANDING (n = 6, m = 2) and the two non-smooth ones
+  # (clip / angle_normalize / jax.grad inside the dynamics: SURVEY 9-14)
+  "y_rocket_trap_10": ("ROCKETLANDING", "COLLOCATION", "TRAPEZOIDAL", "HEUN", 10, 1),
+  "y_rocket_hs_5": ("ROCKETLANDING", "COLLOCATION", "HERMITE_SIMPSON", "RK4", 5, 1),
+  "y_rocket_shooting_3x4_heun": ("ROCKETLANDING", "SHOOTING", "TRAPEZOIDAL", "HEUN", 3, 4),
+  "y_pendulum_trap_20": ("PENDULUM", "COLLOCATION", "TRAPEZOIDAL", "HEUN", 20, 1),
+  "y_pendulum_shooting_50x1_heun": ("PENDULUM", "SHOOTING", "TRAPEZOIDAL", "HEUN", 50, 1),
+  "y_mountaincar_trap_20": ("MOUNTAINCAR", "COLLOCATION", "TRAPEZOIDAL", "HEUN", 20, 1),
+  "y_mountaincar_shooting_4x5_rk4": ("MOUNTAINCAR", "SHOOTING", "TRAPEZOIDAL", "RK4", 4, 5),
   # BASELINE config C5: CARTPOLE with neural-ODE MLP dynamics (3 x 64), planned the way the reference's
   # plan_with_node_model does (myriad/utils.py:230-242: system.dynamics <- net.apply(params, append(x, u))).
   # Weights: tests/golden/node_cartpole_64x64x64.npz (tools/fit_node.py).
@@ -118,6 +127,10 @@ SOLVE_CASES = [
   "x_mould_trap_10", "x_glucose_trap_10", "x_seir_trap_10", "x_hiv_trap_10", "x_bacteria_trap_10", "x_bacteria_shooting_3x5_heun", "x_tumour_trap_10", "x_predprey_shooting_100x1_heun", "x_bear_trap_10", "x_bear_shooting_3x4_heun",  "x_harvest_trap_10", "x_scwb_shooting_4x5_heun",
   # full-size BASELINE configs whose reference solve takes tens of minutes under the shim (generated once, round 2)
   "c2_cartpole_hs_100", "c5_node_cartpole_trap_100",
+  # (ROCKETLANDING and PENDULUM: the reference's own SLSQP ends infeasible -- |c| = 187 / 0.07 -- on these: with m = 2 the
+  #  trapezoid pins node N-1 instead of N and scrambles the control bounds; PENDULUM's target angle pi
+  #  sits on the discontinuity of angle_normalize.  They are covered by the evaluation / rollout fixtures only.)
+  "y_mountaincar_trap_20", "y_mountaincar_shooting_4x5_rk4",
 ]
 
 

@@ -139,6 +139,57 @@ def make_params():
   return out
 
 
+def make_dataset():
+  """Batched dataset rollouts (myriad/utils.py:422-424: integrate_time_independent_in_parallel over all trajectories of
+  a dataset) by the reference code under the shim, for seeded random-walk controls, plus the reference's extragradient
+  iterates (nlp_solvers/extra_gradient.py) on its own test problem (tests/tests.py:253-265)."""
+  from . import refshim
+  refshim.install()
+  from myriad.config import IntegrationMethod
+  from myriad.systems import SystemType
+  from myriad.utils import integrate_time_independent_in_parallel
+  out = {}
+  rng = np.random.Generator(np.random.PCG64(11))
+  for name, steps in (("CARTPOLE", 20), ("VANDERPOL", 30), ("ROCKETLANDING", 12)):
+    system = SystemType[name]()
+    n = system.x_0.shape[0]
+    b = np.asarray(system.bounds, dtype=np.float64)
+    m = b.shape[0] - n
+    total = 6
+    us = rng.uniform(b[n:, 0], b[n:, 1], (total, 2 * steps + 1, m)) * 0.5
+    x0 = np.clip(np.asarray(system.x_0)[None] + 0.1 * rng.standard_normal((total, n)), b[:n, 0], b[:n, 1])
+    out[f"{name}_us"] = us; out[f"{name}_x0"] = x0; out[f"{name}_steps"] = np.int64(steps)
+    for meth in IntegrationMethod:
+      u_in = us if meth == IntegrationMethod.RK4 else us[:, :steps + 1]
+      u_call = u_in if m > 1 else u_in[..., 0]  # the reference squeezes scalar controls (shooting.py:128-129)
+      _, xs = integrate_time_independent_in_parallel(system.dynamics, x0, u_call, system.T / steps, steps, meth)
+      out[f"{name}_{meth.name}_xs"] = np.asarray(xs, dtype=np.float64)
+  return out
+
+
+def make_exgd():
+  """The reference's extragradient solver (nlp_solvers/extra_gradient.py:10-82) run by the reference's own solve() on
+  the problem of its own test (tests/tests.py:253-265: SIMPLECASE, SHOOTING 50 x 1, HEUN), 200 steps."""
+  from . import refshim
+  refshim.install()
+  import contextlib
+  import io
+  from myriad.config import Config, HParams, IntegrationMethod, NLPSolverType, OptimizerType
+  from myriad.nlp_solvers import solve
+  from myriad.systems import SystemType
+  from myriad.trajectory_optimizers import get_optimizer
+  hp = HParams(system=SystemType.SIMPLECASE, optimizer=OptimizerType.SHOOTING, nlpsolver=NLPSolverType.EXTRAGRADIENT,
+               integration_method=IntegrationMethod.HEUN, intervals=50, controls_per_interval=1, max_iter=20)
+  assert hp.max_iter == 200  # config.py:100-101
+  cfg = Config(verbose=False, plot=False)
+  with contextlib.redirect_stdout(io.StringIO()):
+    opt = get_optimizer(hp, cfg, hp.system())
+    res = solve(hp, cfg, {"objective": opt.objective, "guess": opt.guess, "constraints": opt.constraints, "bounds": opt.bounds,
+                          "unravel": opt.unravel})
+  return {"z": np.asarray(res["xs_and_us"]), "lam": np.asarray(res["lambda"]), "cost": np.float64(res["cost"]),
+          "guess": np.asarray(opt.guess), "bounds": np.asarray(opt.bounds)}
+
+
 def main():
   what = sys.argv[1] if len(sys.argv) > 1 else "tight"
   only = sys.argv[2] if len(sys.argv) > 2 else None
@@ -153,6 +204,14 @@ def main():
     fx = make_random()
     np.savez_compressed(os.path.join(GOLD, "random_x0_c2.npz"), **fx)
     print("random rows:", fx["cost"], fx["cost_tight"], fx["success"])
+  elif what == "dataset":
+    fx = make_dataset()
+    np.savez_compressed(os.path.join(GOLD, "dataset_rollouts.npz"), **fx)
+    print({k: np.shape(v) for k, v in fx.items()})
+  elif what == "exgd":
+    fx = make_exgd()
+    np.savez_compressed(os.path.join(GOLD, "exgd_simplecase.npz"), **fx)
+    print("exgd cost", float(fx["cost"]), "lam[:3]", fx["lam"][:3])
   elif what == "params":
     fx = make_params()
     np.savez_compressed(os.path.join(GOLD, "params_cartpole.npz"), **fx)

@@ -49,7 +49,15 @@ class ClampArray(np.ndarray):
 
   def __iter__(self):  # iteration must still stop at the end
     for i in range(self.shape[0]):
-      yield super().__getitem__(i)
+      v = super().__getitem__(i)
+      # complex scalars (complex-step differentiation) stay ClampArrays so that ``%`` below keeps working on them
+      yield np.asarray(v).view(ClampArray) if np.iscomplexobj(v) and np.ndim(v) == 0 else v
+
+  def __mod__(self, other):
+    """jnp.remainder; for complex-step inputs the remainder acts on the real part (its derivative w.r.t. x is 1)"""
+    if np.iscomplexobj(self):
+      return _wrap(np.asarray(self) - np.floor(np.real(np.asarray(self)) / other) * other)
+    return _wrap(np.mod(np.asarray(self), other))
 
 
 def _wrap(v):
@@ -88,8 +96,21 @@ def _make_jnp() -> types.ModuleType:
     except (ValueError, TypeError):
       return _wrap(np.array([np.asarray(e).reshape(()) for e in x], dtype=dtype))
 
+  def clip(x, a_min=None, a_max=None):
+    """jnp.clip with JAX's derivative (1 strictly inside, 0 outside), also for complex-step inputs"""
+    x = np.asarray(x)
+    if not np.iscomplexobj(x):
+      return _wrap(np.clip(x, a_min, a_max))
+    out = x.copy()
+    if a_min is not None:
+      out = np.where(x.real < a_min, a_min + 0j, out)
+    if a_max is not None:
+      out = np.where(x.real > a_max, a_max + 0j, out)
+    return _wrap(out)
+
   jnp.array = array
   jnp.asarray = array
+  jnp.clip = clip
   return jnp
 
 
@@ -108,7 +129,7 @@ def _vmap(fun, in_axes=0, out_axes=0):
         break
     outs = []
     for i in range(n):
-      call = [a if ax is None else np.take(a, i, axis=ax) for a, ax in zip(args, axes)]
+      call = [a if ax is None else _wrap(np.take(a, i, axis=ax)) for a, ax in zip(args, axes)]
       outs.append(fun(*call))
     if isinstance(outs[0], tuple):
       return tuple(np.stack([np.asarray(o[j]) for o in outs]) for j in range(len(outs[0])))
@@ -127,7 +148,7 @@ def _scan(f, init, xs, length=None):
   carry = init
   ys = []
   for x in np.asarray(xs):
-    carry, y = f(carry, x)
+    carry, y = f(_wrap(carry) if isinstance(carry, np.ndarray) else carry, x)
     ys.append(np.asarray(y))
   return carry, np.stack(ys)
 
@@ -144,18 +165,28 @@ def _jacfwd_complex(fun):
     for j in range(z.shape[0]):
       zc = z.astype(np.complex128)
       zc[j] += 1j * _CS_STEP
-      cols.append(np.imag(np.asarray(fun(zc))) / _CS_STEP)
+      cols.append(np.imag(np.asarray(fun(_wrap(zc)))) / _CS_STEP)
     return np.stack(cols, axis=-1)
 
   return jac
 
 
 def _grad(fun, argnums=0):
-  assert argnums == 0
-  j = _jacfwd_complex(fun)
+  """jax.grad of a scalar function w.r.t. positional argument ``argnums`` (complex-step)"""
 
-  def g(z):
-    return np.asarray(j(z)).reshape(-1)
+  def g(*args):
+    z = args[argnums]
+    rest = lambda v: fun(*[v if k == argnums else a for k, a in enumerate(args)])
+    if np.iscomplexobj(z) and np.ndim(z) == 0:
+      # a grad nested inside an outer complex-step differentiation (mountain_car.py:91: jax.grad(hill_function)):
+      # central difference with a real step on the complex point -- exact up to rounding for the quadratic hill
+      # function (:11-13), and it carries the outer imaginary perturbation through
+      h = 1e-3 * max(1.0, abs(complex(z)))
+      return _wrap(np.asarray((rest(z + h) - rest(z - h)) / (2 * h)))
+    if np.ndim(z) == 0:
+      zc = complex(float(z), _CS_STEP)
+      return _wrap(np.asarray(np.imag(rest(zc)) / _CS_STEP))
+    return np.asarray(_jacfwd_complex(rest)(z)).reshape(-1)
 
   return g
 

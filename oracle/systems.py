@@ -404,6 +404,88 @@ def haiku_style_mlp_weights(n_in: int, hidden: Sequence[int], n_out: int, seed: 
   return out
 
 
+def _clip(v, lo, hi):
+  """jnp.clip, also for complex-step inputs (derivative 1 strictly inside, 0 outside) and torch tensors"""
+  if torch is not None and isinstance(v, torch.Tensor):
+    return torch.clamp(v, lo, hi)
+  v = np.asarray(v)
+  if np.iscomplexobj(v):
+    return np.where(v.real < lo, lo + 0j, np.where(v.real > hi, hi + 0j, v))
+  return np.clip(v, lo, hi)
+
+
+def _angle_normalize(x):
+  """pendulum.py:17-18: ((x + pi) % (2 pi)) - pi with jnp.remainder semantics"""
+  if torch is not None and isinstance(x, torch.Tensor):
+    return torch.remainder(x + math.pi, 2 * math.pi) - math.pi
+  x = np.asarray(x)
+  re = x.real if np.iscomplexobj(x) else x
+  return x + math.pi - np.floor((re + math.pi) / (2 * math.pi)) * (2 * math.pi) - math.pi
+
+
+class RocketLanding(OracleSystem):
+  """myriad/systems/miscellaneous/rocket_landing.py:54-124"""
+
+  def __init__(self, g=9.8, m=100_000, length=50, width=10):
+    deg = 0.01745329
+    super().__init__("ROCKETLANDING", np.array([0., 0., 1000., -80., -np.pi / 2., 0.]), np.zeros(6), 16.,
+                     np.array([[-250., 150.], [-250., 150.], [0., 1000.], [-250., 150.], [-2 * np.pi, 2 * np.pi], [-250., 150.],
+                               [0.4, 1.], [-20 * deg, 20 * deg]]), False,
+                     dict(g=g, m=m, length=length, max_thrust=1 * 2210 * 1000))
+
+  def dynamics(self, x, u):
+    xp = _xp(x)
+    p = self.params
+    theta = x[..., 4]
+    thrust, ang = u[..., 0], u[..., 1]
+    Fx = p["max_thrust"] * thrust * xp.sin(ang + theta)           # rocket_landing.py:107
+    Fy = p["max_thrust"] * thrust * xp.cos(ang + theta)           # :112
+    Tq = -p["length"] / 2 * p["max_thrust"] * thrust * xp.sin(ang)  # :117
+    I = 1 / 12 * p["m"] * p["length"] ** 2                        # :62
+    return _stack([x[..., 1], Fx / p["m"], x[..., 3], Fy / p["m"] - p["g"], x[..., 5], Tq / I], x)
+
+  def cost(self, x, u, t):
+    return u[..., 0] ** 2 + u[..., 1] ** 2 + 2 * x[..., 5] ** 2   # :124
+
+
+class Pendulum(OracleSystem):
+  """myriad/systems/classical_control/pendulum.py:50-119 (clipped torque / speed, normalised angle)"""
+
+  def __init__(self, g=10., m=1., length=1.):
+    super().__init__("PENDULUM", np.array([0., 0.]), np.array([np.pi, 0.]), 15.,
+                     np.array([[-np.pi, np.pi], [-8., 8.], [-2., 2.]]), False,
+                     dict(g=g, m=m, length=length, max_speed=8., max_torque=2., ctrl_penalty=0.001))
+
+  def dynamics(self, x, u):
+    xp = _xp(x)
+    p = self.params
+    uu = _clip(u[..., 0], -p["max_torque"], p["max_torque"])      # pendulum.py:97
+    theta = _angle_normalize(x[..., 0])                            # :100
+    dth = _clip(x[..., 1], -p["max_speed"], p["max_speed"])       # :101
+    ddth = (-3. * p["g"] / (2. * p["length"]) * xp.sin(theta) + 3. * uu / (p["m"] * p["length"] ** 2)) * 0.05  # :104-105
+    return _stack([dth, ddth], x)
+
+  def cost(self, x, u, t):
+    p = self.params
+    return _angle_normalize(x[..., 0]) ** 2 + 0.1 * x[..., 1] ** 2 + p["ctrl_penalty"] * u[..., 0] ** 2  # :119
+
+
+class MountainCar(OracleSystem):
+  """myriad/systems/classical_control/mountain_car.py:53-107; hill_function(x) = x^2 / 2 (:11-13)"""
+
+  def __init__(self, power=0.0015, gravity=0.0025):
+    super().__init__("MOUNTAINCAR", np.array([-0.1, 0.]), np.array([0.45, 0.]), 300.,
+                     np.array([[-1.2, 0.6], [-0.07, 0.07], [-1., 1.]]), False, dict(power=power, gravity=gravity))
+
+  def dynamics(self, x, u):
+    p = self.params
+    force = _clip(u[..., 0], -1.0, 1.0)                            # mountain_car.py:88
+    return _stack([x[..., 1], force * p["power"] - p["gravity"] * x[..., 0]], x)  # :90-91
+
+  def cost(self, x, u, t):
+    return 10. * u[..., 0] ** 2                                    # :103
+
+
 SYSTEMS = {
   "SIMPLECASE": SimpleCase,
   "CARTPOLE": CartPole,
@@ -422,6 +504,9 @@ SYSTEMS = {
   "TUMOUR": Tumour,
   "PREDATORPREY": PredatorPrey,
   "BEARPOPULATIONS": BearPopulations,
+  "ROCKETLANDING": RocketLanding,
+  "PENDULUM": Pendulum,
+  "MOUNTAINCAR": MountainCar,
 }
 
 

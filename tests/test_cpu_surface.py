@@ -42,8 +42,10 @@ def test_system_descriptors_match_reference_tables():
   assert np.array_equal(fx["bounds"][4:8, 0], cp.bounds[:4, 0])  # node 1 carries the plain state bounds
   ct = SystemType.CANCERTREATMENT()
   assert ct.x_T is None and ct.T == 20 and np.allclose(ct.x_0, [0.975])
-  with pytest.raises(NotImplementedError):
-    SystemType.ROCKETLANDING()
+  rl = SystemType.ROCKETLANDING()
+  assert rl.state_size == 6 and rl.control_size == 2 and rl.T == 16.0
+  with pytest.raises(NotImplementedError):   # discrete system: rejected like in the reference (base.py:66-67)
+    SystemType.INVASIVEPLANT()
 
 
 def test_shard_ranges_cover_everything():

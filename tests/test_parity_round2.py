@@ -261,3 +261,138 @@ def test_solve_with_params_surface():
   for k in range(3):
     opt2.solve_with_params({**params, "g": 9.0 + 0.1 * k})
   assert len(nlp_solvers._ENGINES) <= max(n0 + 3, nlp_solvers.MAX_ENGINES)
+
+
+# ----------------------------------------------------------------------------- (d) system plugin surface, VJP, datasets, extragradient
+def _abi_call(name, *args):
+  from myriad_b200 import _lib as ML
+  ML.check(getattr(ML.lib(), name)(*args))
+
+
+@pytest.mark.parametrize("sysname", ["CARTPOLE", "VANDERPOL", "ROCKETLANDING", "PENDULUM", "MOUNTAINCAR", "BEARPOPULATIONS", "HARVEST"])
+def test_host_dynamics_and_cost_match_oracle(sysname):
+  """myr_host_dynamics (the generated device code compiled for the host) against the oracle restatement of the
+  reference's dynamics / cost (pinned to the reference by the fixtures), incl. the non-smooth systems' clipped regions."""
+  from myriad_b200 import problems as PR
+  from myriad_b200.systems import SystemType
+  from oracle.systems import make_system
+  system = SystemType[sysname]()
+  osys = make_system(sysname)
+  n, m = system.state_size, system.control_size
+  rng = np.random.default_rng(3)
+  b = np.asarray(system.bounds, dtype=np.float64)
+  lo = np.where(np.isfinite(b[:, 0]), b[:, 0], -2.0); hi = np.where(np.isfinite(b[:, 1]), b[:, 1], 2.0)
+  pts = lo + (hi - lo) * rng.uniform(-0.2, 1.2, (64, n + m))   # 20 % beyond the bounds: exercises clip / angle_normalize
+  x, u = np.ascontiguousarray(pts[:, :n]), np.ascontiguousarray(pts[:, n:])
+  if sysname in ("HARVEST",):
+    x = np.abs(x)
+  t = np.ascontiguousarray(rng.uniform(0, float(system.T), 64))
+  f = np.zeros((64, n)); g = np.zeros(64)
+  d = PR.Transcription(system, PR.TRAPEZOIDAL, "HEUN", 1, 1).desc(device="host")
+  _abi_call("myr_host_dynamics", C.byref(d), 64, _p(x), _p(u), _p(t), _p(f), _p(g))
+  np.testing.assert_allclose(f, osys.dynamics(x, u), rtol=1e-12, atol=1e-13)
+  np.testing.assert_allclose(g, osys.cost(x, u, t), rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.gpu
+def test_system_dynamics_and_cost_methods():
+  """FiniteHorizonControlSystem.dynamics / .cost keep the reference's call signatures (systems/base.py:45-73) and
+  evaluate the generated device code on the GPU."""
+  from myriad_b200.systems import SystemType
+  from oracle.systems import make_system
+  for name in ("CARTPOLE", "ROCKETLANDING", "PENDULUM"):
+    system = SystemType[name]()
+    osys = make_system(name)
+    x = np.asarray(system.x_0, dtype=np.float64) + 0.1
+    u = np.full(system.control_size, 0.3)
+    np.testing.assert_allclose(system.dynamics(x, u), osys.dynamics(x, u), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(system.cost(x, u, 0.5), float(osys.cost(x, u, 0.5)), rtol=1e-12, atol=1e-13)
+    xs = np.stack([x, x + 0.05, x - 0.05])
+    us = np.stack([u, u, u])
+    np.testing.assert_allclose(system.dynamics(xs, us), osys.dynamics(xs, us), rtol=1e-12, atol=1e-13)
+  cp = SystemType.CARTPOLE()
+  pf = dict(g=9.0, m1=1.2, m2=0.4, length=0.6)
+  x = np.array([0.1, 0.2, -0.3, 0.4]); u = np.array([1.5])
+  np.testing.assert_allclose(cp.parametrized_dynamics(pf, x, u), make_system("CARTPOLE", **pf).dynamics(x, u), rtol=1e-12)
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+@pytest.mark.parametrize("case", ["s_cartpole_trap_10", "s_vanderpol_hs_10", "s_cartpole_shooting_5x4_heun", "s_vanderpol_shooting_4x5_rk4",
+                                  "x_bear_shooting_3x4_heun", "y_rocket_trap_10"])
+def test_jtvec_matches_dense_jacobian_of_reference(be, case):
+  """myr_jtvec: J^T lam against the reference's dense jacrev fixture"""
+  from myriad_b200 import _lib as ML
+  fx = load(case)
+  tr = product_transcription(case)
+  rng = np.random.default_rng(4)
+  lam = np.ascontiguousarray(rng.standard_normal((1, tr.ncon)))
+  z = np.ascontiguousarray(fx["z"][None])
+  if be.name == "host":
+    d = tr.desc(device="host")
+    s = ML.problem_sizes(d)
+    f = np.zeros(1); grad = np.zeros((1, s.nvars)); c = np.zeros((1, s.ncon)); J = np.zeros((1, s.jac_block_doubles)); out = np.zeros((1, s.nvars))
+    _abi_call("myr_host_eval", C.byref(d), 1, _p(z), None, _p(f), _p(grad), _p(c), _p(J), None)
+    _abi_call("myr_host_jtvec", C.byref(d), 1, _p(J), _p(lam), _p(out))
+  else:
+    import torch
+    from myriad_b200.engine import Engine
+    eng = Engine(tr.desc())
+    r = eng.eval(torch.as_tensor(z).cuda())
+    out = eng.jtvec(r.Jblk, torch.as_tensor(lam).cuda()).cpu().numpy()
+  np.testing.assert_allclose(out[0], fx["jac_z"].T @ lam[0], rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("be", BACKENDS)
+def test_dataset_rollouts_match_reference(be):
+  """Batched dataset rollouts (myriad/utils.py:422-424, integrate_time_independent_in_parallel) for all four
+  integration methods, incl. the reference's clamp-to-last control indexing."""
+  from myriad_b200 import problems as PR
+  from myriad_b200.systems import SystemType
+  fx = dict(np.load(os.path.join(GOLDEN, "dataset_rollouts.npz")))
+  for name in ("CARTPOLE", "VANDERPOL", "ROCKETLANDING"):
+    system = SystemType[name]()
+    steps = int(fx[f"{name}_steps"])
+    for meth in ("EULER", "HEUN", "MIDPOINT", "RK4"):
+      us = fx[f"{name}_us"] if meth == "RK4" else fx[f"{name}_us"][:, :steps + 1]
+      tr = PR.Transcription(system, PR.TRAPEZOIDAL, meth, steps, 1)
+      xs, _ = be.rollout(tr, us, fx[f"{name}_x0"])
+      np.testing.assert_allclose(xs, fx[f"{name}_{meth}_xs"], rtol=1e-12, atol=1e-12, err_msg=f"{name} {meth}")
+
+
+@pytest.mark.gpu
+def test_generate_dataset_surface():
+  from myriad_b200.config import Config, HParams, OptimizerType
+  from myriad_b200.systems import SystemType
+  from myriad_b200.utils import generate_dataset, get_state_trajectory_and_cost_batch
+  import torch
+  hp = HParams(system=SystemType.CARTPOLE, optimizer=OptimizerType.SHOOTING, intervals=1, controls_per_interval=25, train_size=20)
+  np.random.seed(hp.seed)
+  ds = generate_dataset(hp, Config(verbose=False, plot=False))
+  total = hp.train_size + hp.val_size + hp.test_size
+  assert ds.shape == (total, hp.num_steps + 1, 5)
+  b = np.asarray(hp.system().bounds)
+  assert (ds[..., 4] >= b[4, 0]).all() and (ds[..., 4] <= b[4, 1]).all()
+  # the states ARE the rollouts of the controls (clipped to the state bounds like the reference does, utils.py:429)
+  xs, _ = get_state_trajectory_and_cost_batch(hp, hp.system(), torch.as_tensor(ds[:, 0, :4]).cuda().contiguous(),
+                                              torch.as_tensor(ds[..., 4:]).cuda().contiguous())
+  np.testing.assert_allclose(ds[..., :4], np.clip(xs.cpu().numpy(), b[:4, 0], b[:4, 1]), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLDEN, "exgd_simplecase.npz")), reason="exgd fixture not generated")
+def test_extragradient_matches_reference_iterates():
+  """NLPSolverType.EXTRAGRADIENT: 200 steps of the reference's solver (extra_gradient.py:21-33) on its own test problem
+  (tests/tests.py:253-265) reproduce the reference's iterates."""
+  from myriad_b200.config import Config, HParams, IntegrationMethod, NLPSolverType, OptimizerType
+  from myriad_b200.systems import SystemType
+  from myriad_b200.trajectory_optimizers import get_optimizer
+  fx = dict(np.load(os.path.join(GOLDEN, "exgd_simplecase.npz")))
+  hp = HParams(system=SystemType.SIMPLECASE, optimizer=OptimizerType.SHOOTING, nlpsolver=NLPSolverType.EXTRAGRADIENT,
+               integration_method=IntegrationMethod.HEUN, intervals=50, controls_per_interval=1, max_iter=20)
+  assert hp.max_iter == 200
+  opt = get_optimizer(hp, Config(verbose=False, plot=False), hp.system())
+  np.testing.assert_allclose(opt.guess, fx["guess"], rtol=1e-13, atol=1e-15)
+  res = opt.solve()
+  np.testing.assert_allclose(res["xs_and_us"], fx["z"], rtol=1e-9, atol=1e-10)
+  np.testing.assert_allclose(res["lambda"], fx["lam"], rtol=1e-9, atol=1e-10)
+  np.testing.assert_allclose(res["cost"], float(fx["cost"]), rtol=1e-10)

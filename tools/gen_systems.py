@@ -41,6 +41,11 @@ class Printer(C99CodePrinter):
   def _print_Integer(self, expr):
     return f"{int(expr)}.0"
 
+  def _print_angnorm(self, expr):
+    a = self._print(expr.args[0])
+    # Python-style remainder (result has the sign of the divisor), like jnp.remainder
+    return f"((({a}) + M_PI) - floor((({a}) + M_PI) / (2.0 * M_PI)) * (2.0 * M_PI) - M_PI)"
+
 
 PR = Printer()
 
@@ -58,6 +63,19 @@ def U(m):
 
 
 t = sp.Symbol("t", real=True)
+
+
+def clip(v, lo, hi):
+  """jnp.clip(v, lo, hi) with JAX's sub-gradient choice: derivative 1 strictly inside, 0 outside"""
+  return sp.Piecewise((lo, v < lo), (hi, v > hi), (v, True))
+
+
+class angnorm(sp.Function):
+  """angle_normalize(x) = ((x + pi) % (2 pi)) - pi (pendulum.py:17-18); jnp.remainder has derivative 1 w.r.t. x"""
+  nargs = 1
+
+  def fdiff(self, argindex=1):
+    return sp.Integer(1)
 
 
 def system_defs():
@@ -185,6 +203,35 @@ def system_defs():
   add("BEARPOPULATIONS", 16, 3, 2, [("r", 0.1), ("K", 0.75), ("m_p", 0.5), ("m_f", 0.5), ("c_p", 10000.0), ("c_f", 10.0)],
       bear_f, lambda x, u, t, p: x[2] + p["c_p"] * u[0] ** 2 + p["c_f"] * u[1] ** 2,
       ref="myriad/systems/lenhart/bear_populations.py:71-110")
+  # myriad/systems/miscellaneous/rocket_landing.py:100-124 (n = 6, two controls).  max_thrust and the rod inertia
+  # I = m l^2 / 12 are derived in the constructor (:56-62): max_thrust is a parameter here so that the descriptor carries it
+  def rocket_f(x, u, p):
+    th = x[4]
+    thrust, ang = u[0], u[1]
+    Fx = p["max_thrust"] * thrust * sp.sin(ang + th)
+    Fy = p["max_thrust"] * thrust * sp.cos(ang + th)
+    Tq = -p["length"] / 2 * p["max_thrust"] * thrust * sp.sin(ang)
+    I = sp.Rational(1, 12) * p["m"] * p["length"] ** 2
+    return [x[1], Fx / p["m"], x[3], Fy / p["m"] - p["g"], x[5], Tq / I]
+  add("ROCKETLANDING", 17, 6, 2, [("g", 9.8), ("m", 100000.0), ("length", 50.0), ("max_thrust", 2210000.0)],
+      rocket_f, lambda x, u, t, p: u[0] ** 2 + u[1] ** 2 + 2 * x[5] ** 2,
+      ref="myriad/systems/miscellaneous/rocket_landing.py:100-124")
+
+  # myriad/systems/classical_control/pendulum.py:96-119: clipped torque and speed, normalised angle (non-smooth)
+  def pendulum_f(x, u, p):
+    uu = clip(u[0], -p["max_torque"], p["max_torque"])
+    th = angnorm(x[0])
+    dth = clip(x[1], -p["max_speed"], p["max_speed"])
+    return [dth, (-3 * p["g"] / (2 * p["length"]) * sp.sin(th) + 3 * uu / (p["m"] * p["length"] ** 2)) * sp.Rational(1, 20)]
+  add("PENDULUM", 18, 2, 1, [("g", 10.0), ("m", 1.0), ("length", 1.0), ("max_speed", 8.0), ("max_torque", 2.0), ("ctrl_penalty", 0.001)],
+      pendulum_f, lambda x, u, t, p: angnorm(x[0]) ** 2 + sp.Rational(1, 10) * x[1] ** 2 + p["ctrl_penalty"] * u[0] ** 2,
+      ref="myriad/systems/classical_control/pendulum.py:96-119")
+
+  # myriad/systems/classical_control/mountain_car.py:86-107: hill_function(x) = x^2 / 2 (:11-13), so grad(hill)(x) = x
+  add("MOUNTAINCAR", 19, 2, 1, [("power", 0.0015), ("gravity", 0.0025)],
+      lambda x, u, p: [x[1], clip(u[0], -1, 1) * p["power"] - p["gravity"] * x[0]],
+      lambda x, u, t, p: 10 * u[0] ** 2,
+      ref="myriad/systems/classical_control/mountain_car.py:86-107")
   return S
 
 
