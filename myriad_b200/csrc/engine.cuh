@@ -72,12 +72,12 @@ struct Dims {
 #define MYR_WS_ARRAYS(X)                                                                                              \
   X(crD, St * D::BS) X(crU, St * D::BS) X(crVL, St * D::BS) X(crVU, St * D::BS) X(crb, St * NC) X(dlam, St * NC)       \
   X(Hinv, Q * D::HS) X(G, Q * D::GS) X(F, Q * D::GS)                                                                  \
+  X(dynf, kCoopMlp ? Q * S::n : 0) X(dynJ, kCoopMlp ? Q * S::n * NW : 0) X(dynH, kCoopMlp ? Q * S::NWP : 0)           \
   X(lam, St * NC) X(z, ldq * NW) X(rb, ldq * NW) X(dz, ldq * NW) X(tv, ldq * NW) X(fixm, (Q + 1) / 2)                   \
   X(W, Q * D::WSZ) X(gl, ldq * NW) X(zL, ldq * NW) X(zU, ldq * NW) X(lbr, ldq * NW) X(ubr, ldq * NW)                    \
   X(sig, ldq * NW) X(rsl, ldq * NW) X(rsu, ldq * NW) X(dzL, ldq * NW) X(dzU, ldq * NW) X(zt, ldq * NW)                  \
   X(phi, Q * NC) X(psi, Q * NC) X(c, St * NC) X(sch, St * NC) X(ct, St * NC)                                          \
   X(dz2, ldq * NW) X(csoc, St * NC) X(dl2, St * NC)                                                                   \
-  X(dynf, kCoopMlp ? Q * S::n : 0) X(dynJ, kCoopMlp ? Q * S::n * NW : 0) X(dynH, kCoopMlp ? Q * S::NWP : 0)           \
   X(ext, scheme_is_lifted<S>::value ? 6 * Q * NW + St * NC : 0)
 
 template <class S>
@@ -127,8 +127,10 @@ struct WS {
 #undef X
   double* red;       // reduction scratch: 2 * kRedStride doubles
   double* mlp_scr;   // NODE systems: scratch of the cooperative MLP pass (shared memory), else null
+  int vq0, vi0, vqs, vis;   // VarIter: start (node, component) of this thread and its stride
   MYR_HDI WS(const L& lay, unsigned long long mask, double* smem, double* glob) {
     Q = lay.Q; St = lay.St; ldq = lay.ldq;
+    vi0 = MYR_TID / Q; vq0 = MYR_TID - vi0 * Q; vis = MYR_NT / Q; vqs = MYR_NT - vis * Q;
     double* sp = smem; double* gp = glob;
 #define X(name, sz) if ((mask >> L::A_##name) & 1ull) { name = sp; sp += lay.size[L::A_##name]; } else { name = gp; gp += lay.size[L::A_##name]; }
     MYR_WS_ARRAYS(X)
@@ -137,6 +139,21 @@ struct WS {
   }
   MYR_HDI uint32_t* fix() const { return reinterpret_cast<uint32_t*>(fixm); }
 };
+
+// Flat loop over all variables (node q, component i) of the instance: thread t takes elements t, t + NT, ... of the
+// Q * NW variables (i-major), advanced without integer divisions.  Vector phases use it so that the work spreads over
+// every thread of the CTA (not just one thread per node) and each thread's loads are independent of one another.
+template <class S>
+struct VarIter {
+  int q, i;
+  MYR_HDI explicit VarIter(const WS<S>& ws) : q(ws.vq0), i(ws.vi0) {}
+  MYR_HDI bool valid() const { return i < S::NW; }
+  MYR_HDI void next(const WS<S>& ws) {
+    q += ws.vqs; i += ws.vis;
+    if (q >= ws.Q) { q -= ws.Q; ++i; }
+  }
+};
+#define MYR_FOR_VARS(it) for (VarIter<S> it(ws); it.valid(); it.next(ws))
 
 #define NQ(arr, q, e) ws.arr[(e) * ws.ldq + (q)]
 #define NS(arr, j, r) ws.arr[(j) * NC + (r)]
@@ -157,7 +174,9 @@ MYR_HDI void block_reduce_multi(double* v, double* red, int& parity) {
   static_assert(K <= kRedMaxK, "too many fused reductions");
   constexpr int ops[K] = {OPS...};
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-#pragma unroll
+  // the loops over shuffle distances / warps stay rolled (K independent operations inside): the kernel is
+  // instruction-fetch sensitive and this helper is expanded at every call site
+#pragma unroll 1
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = red_apply(ops[k], v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
@@ -170,10 +189,11 @@ MYR_HDI void block_reduce_multi(double* v, double* red, int& parity) {
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    double r = buf[k];
-    for (int ww = 1; ww < nw; ++ww) r = red_apply(ops[k], r, buf[ww * K + k]);
-    v[k] = r;
+  for (int k = 0; k < K; ++k) v[k] = buf[k];
+#pragma unroll 1
+  for (int ww = 1; ww < nw; ++ww) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = red_apply(ops[k], v[k], buf[ww * K + k]);
   }
 #else
   (void)v; (void)red; (void)parity;
@@ -197,15 +217,20 @@ MYR_HDI Bnd make_bnd(double lb, double ub, double relax) {
 
 // sum of log(slack) accumulated as log(product of slacks): one log per node instead of one per bound.  The product
 // is flushed whenever it leaves [1e-200, 1e200]; a non-positive slack poisons the result with NaN like log() would.
+#ifdef __CUDA_ARCH__
+__device__ __noinline__ double log_outlined(double x) { return log(x); }   // one copy of the (long) log sequence in the kernel
+#else
+inline double log_outlined(double x) { return log(x); }
+#endif
 struct LogProd {
   double prod = 1.0, sum = 0.0;
   bool bad = false;
   MYR_HDI void mul(double s) {
     bad = bad || !(s > 0.0);
     prod *= s;
-    if (!(prod > 1e-200 && prod < 1e200)) { sum += log(prod); prod = 1.0; }
+    if (!(prod > 1e-200 && prod < 1e200)) { sum += log_outlined(prod); prod = 1.0; }
   }
-  MYR_HDI double value() const { return bad ? NAN : sum + log(prod); }
+  MYR_HDI double value() const { return bad ? NAN : sum + log_outlined(prod); }
 };
 
 // multipliers of the slot's lam array as the schemes' node_mu wants them
@@ -327,31 +352,96 @@ struct CrGroup { static constexpr int G = NC <= 1 ? 1 : (NC <= 2 ? 2 : (NC <= 4 
 #define MYR_CR_ROWS(r) for (int r = 0; r < NC; ++r)
 #endif
 
+// reciprocal for pivots: the hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps -- full double accuracy for the
+// normal-range pivots that pass the acceptance tests, a third of the instructions of an IEEE division
+MYR_HDI double pivot_rcp(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / x;
+#endif
+}
+
+// Closed-form inverses with inertia for the block sizes that allow them: N = 1, N = 2 (adjugate) and N = 4 (2 x 2
+// partition: A11 and its Schur complement are inverted as 2 x 2 blocks -- i.e. block pivots, which also handle a zero
+// diagonal entry with a non-zero off-diagonal one, the typical shape of an indefinite block).  Dependent chain: two
+// reciprocals and ~15 multiply-adds, no cross-lane traffic.  M: symmetric N x N row-major (both triangles read and
+// averaged).  ok = false when a block pivot is too small relative to its entries (the caller falls back to the pivoted
+// routine).
+template <int N> struct has_closed_inverse { static constexpr bool value = (N == 1 || N == 2 || N == 4); };
+
+MYR_HDI void inv2_sym(double a, double b, double c, double& x00, double& x01, double& x11, bool& ok, int& np, int& nn) {
+  const double det = a * c - b * b;
+  const double sc = fmax(fmax(fabs(a), fabs(c)), fabs(b));
+  ok = ok && (fabs(det) > 1e-14 * sc * sc) && (fabs(det) > 1e-290);
+  if (det < 0.0) { ++np; ++nn; } else if (a > 0.0) np += 2; else nn += 2;
+  const double r = pivot_rcp(det);
+  x00 = c * r; x01 = -b * r; x11 = a * r;
+}
+
+template <int N>
+MYR_HDI void small_sym_inverse(const double* M, double* X, bool& ok, int& np, int& nn) {
+  ok = true; np = 0; nn = 0;
+  if (N == 1) {
+    const double d = M[0];
+    ok = fabs(d) > 1e-290;
+    if (d > 0.0) ++np; else ++nn;
+    X[0] = pivot_rcp(d);
+  } else if (N == 2) {
+    double x00, x01, x11;
+    inv2_sym(M[0], 0.5 * (M[1] + M[2]), M[3], x00, x01, x11, ok, np, nn);
+    X[0] = x00; X[1] = x01; X[2] = x01; X[3] = x11;
+  } else {
+    const double a00 = M[0], a11 = M[5], a22 = M[10], a33 = M[15];
+    const double a01 = 0.5 * (M[1] + M[4]), a02 = 0.5 * (M[2] + M[8]), a03 = 0.5 * (M[3] + M[12]);
+    const double a12 = 0.5 * (M[6] + M[9]), a13 = 0.5 * (M[7] + M[13]), a23 = 0.5 * (M[11] + M[14]);
+    double p00, p01, p11;                        // A11^-1
+    inv2_sym(a00, a01, a11, p00, p01, p11, ok, np, nn);
+    const double t00 = p00 * a02 + p01 * a12, t01 = p00 * a03 + p01 * a13;   // T = A11^-1 A12
+    const double t10 = p01 * a02 + p11 * a12, t11 = p01 * a03 + p11 * a13;
+    // multiplier growth bound, the block analogue of |l_ik| <= 1e7 in the scalar LDL^T test
+    ok = ok && (fmax(fmax(fabs(t00), fabs(t01)), fmax(fabs(t10), fabs(t11))) <= 1e7);
+    const double s00 = a22 - (a02 * t00 + a12 * t10), s01 = a23 - (a02 * t01 + a12 * t11), s11 = a33 - (a03 * t01 + a13 * t11);
+    double q00, q01, q11;                        // S^-1
+    inv2_sym(s00, s01, s11, q00, q01, q11, ok, np, nn);
+    const double x02 = -(t00 * q00 + t01 * q01), x03 = -(t00 * q01 + t01 * q11);   // X12 = -T S^-1
+    const double x12 = -(t10 * q00 + t11 * q01), x13 = -(t10 * q01 + t11 * q11);
+    const double x00 = p00 - (x02 * t00 + x03 * t01), x01 = p01 - (x02 * t10 + x03 * t11), x11 = p11 - (x12 * t10 + x13 * t11);
+    X[0] = x00; X[1] = x01; X[2] = x02; X[3] = x03;
+    X[4] = x01; X[5] = x11; X[6] = x12; X[7] = x13;
+    X[8] = x02; X[9] = x12; X[10] = q00; X[11] = q01;
+    X[12] = x03; X[13] = x13; X[14] = q01; X[15] = q11;
+  }
+}
+
 // host: full Gauss-Jordan inverse without pivoting, same arithmetic as the cooperative device version
 template <int N>
 inline bool gj_inverse_full(double* a /* N x N in/out */, int& np, int& nn) {
-  double sc = 0.0;
-  for (int i = 0; i < N * N; ++i) sc = fmax(sc, fabs(a[i]));
-  const double tiny = 1e-14 * sc;
   bool ok = true;
   np = nn = 0;
   for (int k = 0; k < N; ++k) {
     double rk[N];
     for (int j = 0; j < N; ++j) rk[j] = a[k * N + j];
     const double p = rk[k];
-    double colmax = 0.0;
-    for (int j = k + 1; j < N; ++j) colmax = fmax(colmax, fabs(rk[j]));
-    ok = ok && (fabs(p) > 1e-7 * colmax) && (fabs(p) > tiny);
+    double colmax = 0.0, rowmax = 0.0;
+    for (int j = 0; j < N; ++j) { const double v = fabs(rk[j]); rowmax = fmax(rowmax, v); if (j > k) colmax = fmax(colmax, v); }
+    ok = ok && (fabs(p) > 1e-7 * colmax) && (fabs(p) > 1e-14 * rowmax) && (fabs(p) > 1e-290);
     if (p > 0) ++np; else ++nn;
-    const double ip = 1.0 / p;
+    const double ip = pivot_rcp(p);
     for (int r = 0; r < N; ++r) {
+      const bool piv = (r == k);
       const double f = a[r * N + k];
       for (int j = 0; j < N; ++j) {
         if (j == k) continue;
         const double s = rk[j] * ip;
-        a[r * N + j] = (r == k) ? s : a[r * N + j] - f * s;
+        a[r * N + j] = piv ? s : a[r * N + j] - f * s;
       }
-      a[r * N + k] = (r == k) ? ip : -f * ip;
+      a[r * N + k] = piv ? ip : -f * ip;
     }
   }
   return ok;
@@ -362,12 +452,6 @@ inline bool gj_inverse_full(double* a /* N x N in/out */, int& np, int& nn) {
 // Must be executed by all 32 lanes of the warp.  ok / np / nn are identical on all lanes of a group.
 template <int N, int G>
 __device__ __forceinline__ void coop_inverse(double (&a)[N], int r, bool& ok, int& np, int& nn) {
-  double sc = 0.0;
-#pragma unroll
-  for (int j = 0; j < N; ++j) sc = fmax(sc, fabs(a[j]));
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) sc = fmax(sc, __shfl_xor_sync(0xffffffffu, sc, o));
-  const double tiny = 1e-14 * sc;
   ok = true; np = 0; nn = 0;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
@@ -375,14 +459,14 @@ __device__ __forceinline__ void coop_inverse(double (&a)[N], int r, bool& ok, in
 #pragma unroll
     for (int j = 0; j < N; ++j) rk[j] = __shfl_sync(0xffffffffu, a[j], k, G);
     const double p = rk[k];
-    double colmax = 0.0;
+    double colmax = 0.0, rowmax = 0.0;
 #pragma unroll
-    for (int j = k + 1; j < N; ++j) colmax = fmax(colmax, fabs(rk[j]));
-    ok = ok && (fabs(p) > 1e-7 * colmax) && (fabs(p) > tiny);
+    for (int j = 0; j < N; ++j) { const double v = fabs(rk[j]); rowmax = fmax(rowmax, v); if (j > k) colmax = fmax(colmax, v); }
+    ok = ok && (fabs(p) > 1e-7 * colmax) && (fabs(p) > 1e-14 * rowmax) && (fabs(p) > 1e-290);
     if (p > 0) ++np; else ++nn;
-    const double ip = 1.0 / p;
-    const double f = a[k];
+    const double ip = pivot_rcp(p);
     const bool piv = (r == k);
+    const double f = a[k];
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       if (j == k) continue;
@@ -420,10 +504,26 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
 #ifdef __CUDA_ARCH__
   auto pivot_row = [&](int i, bool active, double (&a)[NC]) {
     const double* Di = D + i * BS;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) a[c] = rvalid ? Di[rl * NC + c] : (c == 0 ? 1.0 : 0.0);
     bool ok; int p_, n_;
-    coop_inverse<NC, G>(a, rl, ok, p_, n_);
+    if constexpr (has_closed_inverse<NC>::value) {
+      // every lane inverts the whole (small) block redundantly: no cross-lane traffic, and lane rl keeps row rl
+      double M[BB], X[BB];
+#pragma unroll
+      for (int e = 0; e < BB; ++e) M[e] = Di[e];
+      small_sym_inverse<NC>(M, X, ok, p_, n_);
+      ok = ok || !active;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        double v = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < NC; ++rr) v = (rr == rl) ? X[rr * NC + c] : v;
+        a[c] = v;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) a[c] = (rvalid && active) ? Di[rl * NC + c] : (c == rl ? 1.0 : 0.0);
+      coop_inverse<NC, G>(a, rl, ok, p_, n_);
+    }
     int z_ = 0;
     if (!__all_sync(0xffffffffu, ok)) {   // rare: natural-order pivots rejected somewhere in this warp
       if (!ok) {
@@ -452,7 +552,15 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
     const double* Di = D + i * BS;
     for (int e = 0; e < BB; ++e) Dinv[e] = Di[e];
     int p_, n_, z_ = 0;
-    if (!gj_inverse_full<NC>(Dinv, p_, n_)) {
+    bool ok_;
+    if constexpr (has_closed_inverse<NC>::value) {
+      double M[BB];
+      for (int e = 0; e < BB; ++e) M[e] = Di[e];
+      small_sym_inverse<NC>(M, Dinv, ok_, p_, n_);
+    } else {
+      ok_ = gj_inverse_full<NC>(Dinv, p_, n_);
+    }
+    if (!ok_) {
       double A[BB];
       for (int r = 0; r < NC; ++r)
         for (int c = 0; c < NC; ++c) A[r * NC + c] = 0.5 * (Di[r * NC + c] + Di[c * NC + r]);
@@ -461,10 +569,10 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
     cp += p_; cn += n_; cz += z_;
   };
 #endif
-  int s = 1;
-  for (; s < St; s <<= 1) {
-    const int nodd = (St - s + 2 * s - 1) / (2 * s);   // blocks i = (2k+1) s < St
-    const int neven = (St + 2 * s - 1) / (2 * s);      // blocks i = 2k s < St
+  int s = 1, ls = 0;   // s = 2^ls
+  for (; s < St; s <<= 1, ++ls) {
+    const int nodd = (St + s - 1) >> (ls + 1);          // blocks i = (2k+1) s < St
+    const int neven = (St + 2 * s - 1) >> (ls + 1);     // blocks i = 2k s < St
     // ---- eliminate the odd blocks: Dinv_i (kept in D), VL_i = Dinv_i U_{i-s}^T, VU_i = Dinv_i U_i, x_i = Dinv_i b_i
     for (int k0 = 0; k0 < nodd; k0 += ngrp) {   // trip count uniform across the CTA (the body contains warp shuffles)
       const int k = k0 + grp;
@@ -587,8 +695,8 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
   }
   MYR_SYNC();
   // ---- back substitution: x_i = (Dinv_i b_i) - VL_i x_{i-s} - VU_i x_{i+s}
-  for (s >>= 1; s >= 1; s >>= 1) {
-    const int nodd = (St - s + 2 * s - 1) / (2 * s);
+  for (s >>= 1, --ls; s >= 1; s >>= 1, --ls) {
+    const int nodd = (St + s - 1) >> (ls + 1);
     for (int k = grp; k < nodd; k += ngrp) {
       const int i = (2 * k + 1) * s;
       MYR_CR_ROWS(r) {
@@ -883,11 +991,13 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
   return (Hzero == 0) && (Szero == 0) && (Sneg == Hneg);
 }
 
-// dz = -(tv + Hinv J^T dl) for the multiplier step dl (stage-major), tv = Hinv rb; written to the node vector dst
+// dz = -(tv + Hinv J^T dl) for the multiplier step dl (stage-major), tv = Hinv rb; written to the node vector dst.
+// Returns this thread's part of  dz^T H dz = -dz . (rb + J^T dl)  (H dz = -(rb + J^T dl) on the free variables).
 template <class S>
-MYR_HDI void kkt_backsub(const Problem& P, const WS<S>& ws, const double* dl, double* dst) {
+MYR_HDI double kkt_backsub(const Problem& P, const WS<S>& ws, const double* dl, double* dst) {
   using D = Dims<S>;
   constexpr int NW = S::NW;
+  double dHd = 0.0;
   for (int q = MYR_TID; q < ws.Q; q += MYR_NT) {
     double u[NW];
     jt_times<S>(P, ws, q, dl, u);
@@ -898,8 +1008,10 @@ MYR_HDI void kkt_backsub(const Problem& P, const WS<S>& ws, const double* dl, do
 #pragma unroll
       for (int k = 0; k < NW; ++k) a += Hq[i * NW + k] * u[k];
       dst[i * ws.ldq + q] = -a;
+      dHd += a * (NQ(rb, q, i) + u[i]);   // a = -dz_i (zero on fixed variables: their rows of Hinv vanish)
     }
   }
+  return dHd;
 }
 
 // Iterative refinement against the matrix WITHOUT delta_reg: the node blocks are factorised with a tiny
@@ -996,11 +1108,13 @@ MYR_HDI void kkt_refine(const Problem& P, const WS<S>& ws, double delta_w, doubl
 
 // complete KKT solve (factor, multipliers, primal step, optional refinement): what myr_kkt_solve exposes
 template <class S>
-MYR_HDI bool kkt_solve(const Problem& P, const WS<S>& ws, double delta_w, double delta_c, double delta_reg, int max_refine, int& parity) {
+MYR_HDI bool kkt_solve(const Problem& P, const WS<S>& ws, double delta_w, double delta_c, double delta_reg, int max_refine, int& parity,
+                       double* dHd_part = nullptr) {
   double minpr;
   const bool ok = kkt_factor<S>(P, ws, delta_w, delta_c, delta_reg, minpr, parity);
   if (!ok) return false;
-  kkt_backsub<S>(P, ws, ws.dlam, ws.dz);
+  const double dHd = kkt_backsub<S>(P, ws, ws.dlam, ws.dz);
+  if (dHd_part) *dHd_part = dHd;
   MYR_SYNC();
   // refinement is only worth its cost when some node block was close to singular
   if (max_refine > 0 && minpr < 1e-4) kkt_refine<S>(P, ws, delta_w, delta_c, max_refine, parity);
@@ -1102,23 +1216,23 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     stage_constraints<S>(P, ws, ws.c, cmx, csm);
     for (int k = MYR_TID; k < ncn; k += MYR_NT) suml += fabs(ws.lam[k]);
     double rdmax = 0.0, szmax = -INFINITY, szmin = INFINITY, sumz = 0.0, nbnd = 0.0, slog = 0.0;
-    for (int q = MYR_TID; q < Q; q += MYR_NT) {
-      const uint32_t fm = ws.fix()[q];
+    {
       LogProd lpq;
-#pragma unroll
-      for (int i = 0; i < NW; ++i) {
-        const bool fixed = (fm >> i) & 1u;
+      MYR_FOR_VARS(it) {
+        const int q = it.q, i = it.i;
+        const bool fixed = (ws.fix()[q] >> i) & 1u;
+        // all loads first, unconditionally: vectors that live in global memory cost one round trip, not one per branch
+        const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = NQ(z, q, i), zl = NQ(zL, q, i), zu = NQ(zU, q, i), r0 = NQ(rb, q, i);
         double rd = 0.0;
         if (!fixed) {
-          const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = NQ(z, q, i), zl = NQ(zL, q, i), zu = NQ(zU, q, i);
-          rd = NQ(rb, q, i) - zl + zu;
+          rd = r0 - zl + zu;
           if (lo > -INFINITY) { const double sl = x - lo; const double pz = sl * zl; szmax = fmax(szmax, pz); szmin = fmin(szmin, pz); sumz += zl; nbnd += 1.0; lpq.mul(sl); }
           if (hi < INFINITY) { const double su = hi - x; const double pz = su * zu; szmax = fmax(szmax, pz); szmin = fmin(szmin, pz); sumz += zu; nbnd += 1.0; lpq.mul(su); }
         }
         const double a = (rd != rd) ? INFINITY : fabs(rd);
         rdmax = fmax(rdmax, a);
       }
-      slog += lpq.value();
+      slog = lpq.value();
     }
     {
       double rv[10] = {fpart, cmx, csm, rdmax, szmax, szmin, sumz, nbnd, slog, suml};
@@ -1144,31 +1258,28 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
 
     MYR_PH(1);
     // ---------------- barrier gradient rb and Sigma (reciprocal slacks are kept for the step-size phase)
-    for (int q = MYR_TID; q < Q; q += MYR_NT) {
-      const uint32_t fm = ws.fix()[q];
-#pragma unroll
-      for (int i = 0; i < NW; ++i) {
-        const bool fixed = (fm >> i) & 1u;
-        double sg = 0.0, rbv = NQ(rb, q, i), r1 = 0.0, r2 = 0.0;
-        if (!fixed) {
-          const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = NQ(z, q, i);
-          if (lo > -INFINITY) { r1 = 1.0 / (x - lo); sg += NQ(zL, q, i) * r1; rbv -= mu * r1; }
-          if (hi < INFINITY) { r2 = 1.0 / (hi - x); sg += NQ(zU, q, i) * r2; rbv += mu * r2; }
-        }
-        NQ(rsl, q, i) = r1; NQ(rsu, q, i) = r2;
-        NQ(sig, q, i) = sg;
-        NQ(rb, q, i) = fixed ? 0.0 : rbv;
+    MYR_FOR_VARS(it) {
+      const int q = it.q, i = it.i;
+      const bool fixed = (ws.fix()[q] >> i) & 1u;
+      const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = NQ(z, q, i), zl = NQ(zL, q, i), zu = NQ(zU, q, i);
+      double sg = 0.0, rbv = NQ(rb, q, i), r1 = 0.0, r2 = 0.0;
+      if (!fixed) {
+        if (lo > -INFINITY) { r1 = 1.0 / (x - lo); sg += zl * r1; rbv -= mu * r1; }
+        if (hi < INFINITY) { r2 = 1.0 / (hi - x); sg += zu * r2; rbv += mu * r2; }
       }
+      NQ(rsl, q, i) = r1; NQ(rsu, q, i) = r2;
+      NQ(sig, q, i) = sg;
+      NQ(rb, q, i) = fixed ? 0.0 : rbv;
     }
-    // (no barrier: the node phase of kkt_factor reads sig / rb of the thread's own nodes)
+    MYR_SYNC();   // the node phase of kkt_factor reads sig / rb of whole nodes
 
     MYR_PH(2);
     // ---------------- K2: KKT solve with inertia correction (IPOPT Algorithm IC)
-    double delta = 0.0;
+    double delta = 0.0, dHd = 0.0;   // dHd: this thread's part of dz^T H dz, from the back-substitution
     bool ok = false;
     for (int tries = 0; tries < 60; ++tries) {
       // accurate steps only matter near the solution: refine the linear solve in the end game only
-      ok = kkt_solve<S>(P, ws, delta, O.delta_c, O.delta_reg, E0 < 1e-3 ? O.max_refine : 0, parity);
+      ok = kkt_solve<S>(P, ws, delta, O.delta_c, O.delta_reg, E0 < 1e-3 ? O.max_refine : 0, parity, &dHd);
       if (ok) break;
       if (delta == 0.0) delta = (delta_last == 0.0) ? O.delta_0 : fmax(O.delta_min, O.kappa_w_minus * delta_last);
       else delta *= (delta_last == 0.0) ? O.kappa_w_plus_first : O.kappa_w_plus;
@@ -1180,39 +1291,28 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     MYR_PH(3);
     // ---------------- step sizes (fraction to the boundary), bound-multiplier steps, merit derivative
     // alpha = min(1, tau / max_i(-d_i / slack_i)): one division at the end instead of one per variable
-    double m_pr = 0.0, m_du = 0.0, dphi = 0.0, dHd = 0.0;
-    for (int q = MYR_TID; q < Q; q += MYR_NT) {
-      double jt[NW];
-      jt_times<S>(P, ws, q, ws.dlam, jt);
-      const uint32_t fm = ws.fix()[q];
-#pragma unroll
-      for (int i = 0; i < NW; ++i) {
-        const bool fixed = (fm >> i) & 1u;
-        const double d = NQ(dz, q, i);
-        double dl = 0.0, du = 0.0;
-        if (!fixed) {
-          const double rbv = NQ(rb, q, i);
-          // H dz = -(rb + J^T dlam):  dz^T H dz = -dz.(rb + J^T dlam)
-          dHd -= d * (rbv + jt[i]);
-          const double r1 = NQ(rsl, q, i), r2 = NQ(rsu, q, i);
-          // barrier-objective gradient = grad f - mu / s_L + mu / s_U
-          dphi += d * (NQ(gl, q, i) - mu * r1 + mu * r2);
-          if (r1 != 0.0) {
-            const double zl = NQ(zL, q, i);
-            dl = mu * r1 - zl - zl * r1 * d;
-            m_pr = fmax(m_pr, -d * r1);
-            if (dl < 0.0) m_du = fmax(m_du, -dl / zl);
-          }
-          if (r2 != 0.0) {
-            const double zu = NQ(zU, q, i);
-            du = mu * r2 - zu + zu * r2 * d;
-            m_pr = fmax(m_pr, d * r2);
-            if (du < 0.0) m_du = fmax(m_du, -du / zu);
-          }
+    double m_pr = 0.0, m_du = 0.0, dphi = 0.0;
+    MYR_FOR_VARS(it) {
+      const int q = it.q, i = it.i;
+      const bool fixed = (ws.fix()[q] >> i) & 1u;
+      const double d = NQ(dz, q, i), r1 = NQ(rsl, q, i), r2 = NQ(rsu, q, i), zl = NQ(zL, q, i), zu = NQ(zU, q, i), g0 = NQ(gl, q, i);
+      double dl = 0.0, du = 0.0;
+      if (!fixed) {
+        // barrier-objective gradient = grad f - mu / s_L + mu / s_U
+        dphi += d * (g0 - mu * r1 + mu * r2);
+        if (r1 != 0.0) {
+          dl = mu * r1 - zl - zl * r1 * d;
+          m_pr = fmax(m_pr, -d * r1);
+          if (dl < 0.0) m_du = fmax(m_du, -dl / zl);
         }
-        NQ(dzL, q, i) = dl;
-        NQ(dzU, q, i) = du;
+        if (r2 != 0.0) {
+          du = mu * r2 - zu + zu * r2 * d;
+          m_pr = fmax(m_pr, d * r2);
+          if (du < 0.0) m_du = fmax(m_du, -du / zu);
+        }
       }
+      NQ(dzL, q, i) = dl;
+      NQ(dzU, q, i) = du;
     }
     {
       double rv[4] = {m_pr, m_du, dphi, dHd};
@@ -1245,12 +1345,9 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       if (soc) {
         kkt_soc_solve<S>(P, ws);
         double m2 = 0.0;
-        for (int q = MYR_TID; q < Q; q += MYR_NT) {
-#pragma unroll
-          for (int i = 0; i < NW; ++i) {
-            const double d = NQ(dz2, q, i);
-            m2 = fmax(m2, fmax(-d * NQ(rsl, q, i), d * NQ(rsu, q, i)));
-          }
+        MYR_FOR_VARS(it) {
+          const double d = NQ(dz2, it.q, it.i);
+          m2 = fmax(m2, fmax(-d * NQ(rsl, it.q, it.i), d * NQ(rsu, it.q, it.i)));
         }
         double rv[1] = {m2};
         block_reduce_multi<R_MAX>(rv, ws.red, parity);
@@ -1262,23 +1359,21 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       ls_used = ls;
       // ---- trial point z + a * step, its barrier log-sum, objective and constraints
       double blog = 0.0;
-      for (int q = MYR_TID; q < Q; q += MYR_NT) {
-        const uint32_t fm = ws.fix()[q];
+      {
         LogProd lpq;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
+        MYR_FOR_VARS(it) {
+          const int q = it.q, i = it.i;
+          const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i);
           const double x = NQ(z, q, i) + a * step[i * ws.ldq + q];
           NQ(zt, q, i) = x;
-          if (!((fm >> i) & 1u)) {
-            const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i);
+          if (!((ws.fix()[q] >> i) & 1u)) {
             if (lo > -INFINITY) lpq.mul(x - lo);
             if (hi < INFINITY) lpq.mul(hi - x);
           }
         }
-        blog += lpq.value();
+        blog = lpq.value();
       }
-      // (no barrier: eval_nodes reads the trial point of the thread's own nodes -- except the cooperative MLP pass)
-      if (Layout<S>::kCoopMlp) MYR_SYNC();
+      MYR_SYNC();   // eval_nodes reads whole nodes of the trial point
       const double ft_part = eval_nodes<S, 0>(P, ws, ws.zt);
       MYR_SYNC();
       double ci_t = 0.0, c1_t = 0.0;
@@ -1326,26 +1421,19 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
 
     MYR_PH(5);
     // ---------------- accept: primal, equality multipliers, bound multipliers (with the kappa_sigma safeguard)
-    for (int q = MYR_TID; q < Q; q += MYR_NT) {
-      const uint32_t fm = ws.fix()[q];
-#pragma unroll
-      for (int i = 0; i < NW; ++i) {
-        if ((fm >> i) & 1u) continue;
-        const double x = NQ(zt, q, i);
-        NQ(z, q, i) = x;
-        const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i);
-        if (lo > -INFINITY) {
-          const double ms = mu / (x - lo);
-          double v = NQ(zL, q, i) + a_du * NQ(dzL, q, i);
-          v = fmax(fmin(v, O.kappa_sigma * ms), ms / O.kappa_sigma);
-          NQ(zL, q, i) = v;
-        }
-        if (hi < INFINITY) {
-          const double ms = mu / (hi - x);
-          double v = NQ(zU, q, i) + a_du * NQ(dzU, q, i);
-          v = fmax(fmin(v, O.kappa_sigma * ms), ms / O.kappa_sigma);
-          NQ(zU, q, i) = v;
-        }
+    MYR_FOR_VARS(it) {
+      const int q = it.q, i = it.i;
+      if ((ws.fix()[q] >> i) & 1u) continue;
+      const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = NQ(zt, q, i);
+      const double zl = NQ(zL, q, i), zu = NQ(zU, q, i), dl = NQ(dzL, q, i), du = NQ(dzU, q, i);
+      NQ(z, q, i) = x;
+      if (lo > -INFINITY) {
+        const double ms = mu / (x - lo);
+        NQ(zL, q, i) = fmax(fmin(zl + a_du * dl, O.kappa_sigma * ms), ms / O.kappa_sigma);
+      }
+      if (hi < INFINITY) {
+        const double ms = mu / (hi - x);
+        NQ(zU, q, i) = fmax(fmin(zu + a_du * du, O.kappa_sigma * ms), ms / O.kappa_sigma);
       }
     }
     for (int k = MYR_TID; k < ncn; k += MYR_NT) ws.lam[k] += alpha * dl_acc[k];

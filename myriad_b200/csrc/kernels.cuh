@@ -481,7 +481,14 @@ struct IpmLaunch {
   static constexpr bool kWide = Layout<S>::kCoopMlp || S::kMaxStageNodes >= 3;
   static constexpr int kThreads = kWide ? 256 : MYR_IPM_THREADS;
   static constexpr int kMinBlocks = kWide ? 1 : MYR_IPM_MINBLOCKS;
-  static int threads(int Q) { const int t = threads_for(Q, Layout<S>::kCoopMlp); return t < kThreads ? t : kThreads; }
+  // one thread per variable (the vector phases are flat loops over the Q * NW variables), at least one per node
+  static int threads(int Q) {
+    if (Layout<S>::kCoopMlp) return kThreads;
+    int t = (Q * S::NW + 31) / 32 * 32;
+    const int tq = (Q + 31) / 32 * 32;
+    if (t < tq) t = tq;
+    return t < kThreads ? t : kThreads;
+  }
 };
 
 // Which arrays of the slot live in shared memory (engine.cuh, "Memory plan") and how many CTAs per SM that allows.

@@ -29,11 +29,26 @@ def pack_solution(z: torch.Tensor, lam: torch.Tensor, obj: torch.Tensor, cost: t
 
 
 def gather_solutions(packed: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
-  """The single collective of the path: all ranks end up with every instance's packed solution, in global row order
-  (equal shard sizes).  No-op without an initialised process group."""
+  """The single collective of the path: all ranks end up with every instance's packed solution, in global row order.
+  Shards may differ in size by one row (shard_range): equal shards take one all_gather_into_tensor, unequal ones are
+  padded to the largest shard and trimmed.  No-op without an initialised process group."""
   if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
     return packed
-  if out is None:
-    out = torch.empty(packed.shape[0] * dist.get_world_size(), packed.shape[1], dtype=packed.dtype, device=packed.device)
-  dist.all_gather_into_tensor(out, packed)
-  return out
+  w = dist.get_world_size()
+  rows = torch.tensor([packed.shape[0]], dtype=torch.int64, device=packed.device)
+  if out is not None and out.shape[0] == packed.shape[0] * w:
+    dist.all_gather_into_tensor(out, packed)   # caller vouches for equal shards (the benchmark's weak-scaling layout)
+    return out
+  all_rows = torch.empty(w, dtype=torch.int64, device=packed.device)
+  dist.all_gather_into_tensor(all_rows, rows)
+  counts = [int(v) for v in all_rows.cpu()]
+  mx = max(counts)
+  if all(c == mx for c in counts):
+    res = torch.empty(mx * w, packed.shape[1], dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(res, packed)
+    return res
+  pad = torch.zeros(mx, packed.shape[1], dtype=packed.dtype, device=packed.device)
+  pad[:packed.shape[0]] = packed
+  buf = torch.empty(mx * w, packed.shape[1], dtype=packed.dtype, device=packed.device)
+  dist.all_gather_into_tensor(buf, pad)
+  return torch.cat([buf[r * mx: r * mx + c] for r, c in enumerate(counts)], dim=0)

@@ -65,12 +65,12 @@ def _gloo_worker(rank, world, port, q):
   from myriad_b200 import _lib as ML
   from myriad_b200 import distributed as D
   dist.init_process_group("gloo", rank=rank, world_size=world)
-  # shard 4 CARTPOLE N=10 instances over 2 ranks; solve each shard with the HOST twin; gather once
+  # shard 5 CARTPOLE N=10 instances over 2 ranks (UNEQUAL shards: 3 + 2); solve each shard with the HOST twin; gather once
   from tests.test_cpu_abi_and_twin import _host_ipm
   d = ML.make_desc("CARTPOLE", ML.OPT_TRAPEZOIDAL, "HEUN", 10)
   s = ML.problem_sizes(d)
-  z0, lb, ub = _tiny_batch(4)
-  lo, hi = D.shard_range(4, rank, world)
+  z0, lb, ub = _tiny_batch(5)
+  lo, hi = D.shard_range(5, rank, world)
   out = _host_ipm(ML, d, s, np.ascontiguousarray(z0[lo:hi]), np.ascontiguousarray(lb[lo:hi]), np.ascontiguousarray(ub[lo:hi]))
   t = lambda a: torch.as_tensor(a)
   packed = D.pack_solution(t(out["z"]), t(out["lam"]), t(out["obj"]), t(out["obj"]), t(out["status"]), t(out["iters"]))
@@ -115,9 +115,9 @@ def test_two_rank_shard_and_gather_gloo():
   from tests.test_cpu_abi_and_twin import _host_ipm
   d = ML.make_desc("CARTPOLE", ML.OPT_TRAPEZOIDAL, "HEUN", 10)
   s = ML.problem_sizes(d)
-  z0, lb, ub = _tiny_batch(4)
+  z0, lb, ub = _tiny_batch(5)
   out = _host_ipm(ML, d, s, z0, lb, ub)
-  assert got.shape == (4, s.nvars + s.ncon + 4)
+  assert got.shape == (5, s.nvars + s.ncon + 4)
   np.testing.assert_array_equal(got[:, :s.nvars], out["z"])
   np.testing.assert_array_equal(got[:, -2], out["status"].astype(np.float64))
   assert (out["status"] == 0).all()

@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
 : > gpurun_out/ab.log
 timeout 300 python tools/ab_bench.py trap,hs >> gpurun_out/ab.log 2>&1
 echo "MYR_IPM_CTAS=1" >> gpurun_out/ab.log; MYR_IPM_CTAS=1 timeout 200 python tools/ab_bench.py trap >> gpurun_out/ab.log 2>&1
