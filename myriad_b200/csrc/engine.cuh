@@ -127,6 +127,7 @@ struct WS {
 #undef X
   double* red;       // reduction scratch: 2 * kRedStride doubles
   double* mlp_scr;   // NODE systems: scratch of the cooperative MLP pass (shared memory), else null
+  const double* theta;   // NODE systems: shared-memory copy of the MLP weights (null: read the caller's vector)
   int vq0, vi0, vqs, vis;   // VarIter: start (node, component) of this thread and its stride
   MYR_HDI WS(const L& lay, unsigned long long mask, double* smem, double* glob) {
     Q = lay.Q; St = lay.St; ldq = lay.ldq;
@@ -135,7 +136,7 @@ struct WS {
 #define X(name, sz) if ((mask >> L::A_##name) & 1ull) { name = sp; sp += lay.size[L::A_##name]; } else { name = gp; gp += lay.size[L::A_##name]; }
     MYR_WS_ARRAYS(X)
 #undef X
-    red = nullptr; mlp_scr = nullptr;
+    red = nullptr; mlp_scr = nullptr; theta = nullptr;
   }
   MYR_HDI uint32_t* fix() const { return reinterpret_cast<uint32_t*>(fixm); }
 };
@@ -258,7 +259,7 @@ MYR_HDI double eval_nodes(const Problem& P, const WS<S>& ws, const double* zv) {
   bool have_pre = false;
 #ifdef __CUDA_ARCH__
   if constexpr (Layout<S>::kCoopMlp) {
-    mlp_nodes_pass<S, MODE>(P, Q, WsZView{zv, ws.ldq}, WsLamView<NC>{ws.lam}, ws.dynf, ws.dynJ, ws.dynH, ws.mlp_scr);
+    mlp_nodes_pass<S, MODE>(P, Q, WsZView{zv, ws.ldq}, WsLamView<NC>{ws.lam}, ws.dynf, ws.dynJ, ws.dynH, ws.mlp_scr, ws.theta);
     have_pre = true;
   }
 #endif
@@ -377,8 +378,9 @@ template <int N> struct has_closed_inverse { static constexpr bool value = (N ==
 
 MYR_HDI void inv2_sym(double a, double b, double c, double& x00, double& x01, double& x11, bool& ok, int& np, int& nn) {
   const double det = a * c - b * b;
-  const double sc = fmax(fmax(fabs(a), fabs(c)), fabs(b));
-  ok = ok && (fabs(det) > 1e-14 * sc * sc) && (fabs(det) > 1e-290);
+  // the adjugate formula loses eps * (|ac| + b^2) / |det| digits to the cancellation in det: accept it only while that
+  // stays below ~1e-9 (invariant under diagonal scaling, so merely badly SCALED blocks still take the fast path)
+  ok = ok && (fabs(det) > 1e-7 * (fabs(a * c) + b * b)) && (fabs(det) > 1e-290);
   if (det < 0.0) { ++np; ++nn; } else if (a > 0.0) np += 2; else nn += 2;
   const double r = pivot_rcp(det);
   x00 = c * r; x01 = -b * r; x11 = a * r;

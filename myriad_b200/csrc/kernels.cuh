@@ -496,11 +496,19 @@ struct IpmLaunch {
 template <class S>
 struct SlotPlan {
   unsigned long long mask;
-  int smem_doubles, glob_doubles, ctas_per_sm;
+  int smem_doubles, glob_doubles, ctas_per_sm, theta_doubles;
   size_t fixed_bytes, smem_bytes;
   explicit SlotPlan(const Problem& P, int max_ctas) {
     const Layout<S> L(P);
-    const size_t mlp = Layout<S>::kCoopMlp ? (size_t)mlp_scratch_doubles<S>(P.mlp) * sizeof(double) : 0;
+    // NODE systems: the cooperative MLP pass's scratch AND a copy of the weights (70 KB for 3 x 64): every node group
+    // re-reads every weight, and with shared memory carved out to the maximum the L1 that used to hold them is gone
+    size_t mlp = 0;
+    theta_doubles = 0;
+    if (Layout<S>::kCoopMlp) {
+      const MlpDesc& M = P.mlp;
+      theta_doubles = (M.boff[M.L - 1] + M.size[M.L] + 1) & ~1;
+      mlp = (size_t)(mlp_scratch_doubles<S>(P.mlp) + theta_doubles) * sizeof(double);
+    }
     fixed_bytes = 2 * kRedStride * sizeof(double) + mlp;
     auto budget = [&](int k) -> long long {
       long long per = 233472 / k - 1024;
@@ -691,13 +699,20 @@ inline IpmOpts make_opts(const MyrIpmOpts* o) {
 // assignment would leave SMs idle at the tail) and solves it in its own workspace slot.
 template <class S>
 __global__ void __launch_bounds__(IpmLaunch<S>::kThreads, IpmLaunch<S>::kMinBlocks)
-ipm_kernel(Problem P, IpmOpts O, IpmIO io, unsigned long long mask, int smem_doubles, double* work, long long slot_stride, int* counter) {
+ipm_kernel(Problem P, IpmOpts O, IpmIO io, unsigned long long mask, int smem_doubles, int theta_doubles, double* work, long long slot_stride,
+           int* counter) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_next;
   const Layout<S> L(P);
   WS<S> ws(L, mask, smem + 2 * kRedStride, work + (long long)blockIdx.x * slot_stride);
   ws.red = smem;
-  ws.mlp_scr = smem + 2 * kRedStride + smem_doubles;
+  ws.mlp_scr = smem + 2 * kRedStride + smem_doubles + theta_doubles;
+  if (Layout<S>::kCoopMlp) {   // weights into shared memory once per (persistent) CTA
+    double* th = smem + 2 * kRedStride + smem_doubles;
+    for (int e = threadIdx.x; e < theta_doubles; e += blockDim.x) th[e] = e < P.mlp.boff[P.mlp.L - 1] + P.mlp.size[P.mlp.L] ? P.mlp.theta[e] : 0.0;
+    ws.theta = th;
+    __syncthreads();
+  }
   while (true) {
     if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
     __syncthreads();
@@ -728,8 +743,8 @@ int sys_ipm_solve(const MyrDesc* desc, const MyrIpmOpts* opts, int B, const doub
     const IpmOpts O = make_opts(opts);
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(ws, 0, MYR_WS_HEADER * sizeof(double), st) != cudaSuccess) return cuda_check("myr_ipm_solve(memset)");
-    ipm_kernel<S><<<grid, threads, sp.smem_bytes, st>>>(P, O, io, sp.mask, sp.smem_doubles, ws + MYR_WS_HEADER, sp.glob_doubles,
-                                                         reinterpret_cast<int*>(ws));
+    ipm_kernel<S><<<grid, threads, sp.smem_bytes, st>>>(P, O, io, sp.mask, sp.smem_doubles, sp.theta_doubles, ws + MYR_WS_HEADER,
+                                                         sp.glob_doubles, reinterpret_cast<int*>(ws));
     return cuda_check("myr_ipm_solve");
   });
 }

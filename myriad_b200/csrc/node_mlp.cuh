@@ -219,11 +219,12 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 // z(q, i): variable i of node q; lam(j, r): multiplier of row r of stage j (views over the caller's layout)
 template <class S, int MODE, class ZView, class LamView>
 __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const ZView z, const LamView lam, double* dynf, double* dynJ,
-                                            double* dynH, double* scr) {
+                                            double* dynH, double* scr, const double* theta_override = nullptr) {
 #ifdef __CUDA_ARCH__
   constexpr int NW = S::NW, n = S::n, NWP = S::NWP;
   constexpr int kRounds = 2;
   const MlpDesc& M = P.mlp;
+  const double* const theta = theta_override ? theta_override : M.theta;   // weights: the caller's vector or a shared-memory copy
   const int Lh = M.L - 1, Hp = M.hp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -256,8 +257,8 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const ZView
     // ---- F: values
     for (int j = 0; j < Lh; ++j) {
       const int in = M.size[j], out = M.size[j + 1];
-      const double* w = M.theta + M.woff[j];
-      const double* b = M.theta + M.boff[j];
+      const double* w = theta + M.woff[j];
+      const double* b = theta + M.boff[j];
       const double* Bs = j == 0 ? in0 : act + (j - 1) * Hp * 8;
       const int KS = mlp_round_up(in, 4) >> 2, MT = mlp_round_up(out, 8) >> 3;
       for (int mt = warp; mt < MT; mt += nwarp) {
@@ -265,7 +266,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const ZView
         double c0 = o < out ? b[o] : 0.0, c1 = c0;
         _Pragma("unroll 4") for (int ks = 0; ks < KS; ++ks) {
           const int i = 4 * ks + t;
-          const double a = (i < in && o < out) ? __ldg(w + i * out + o) : 0.0;
+          const double a = (i < in && o < out) ? (*(w + i * out + o)) : 0.0;
           dmma_m8n8k4(c0, c1, a, Bs[i * 8 + g]);
         }
         double* dst = act + j * Hp * 8 + o * 8 + 2 * t;
@@ -275,8 +276,8 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const ZView
     }
     {  // output layer: y = W_Lh^T h_Lh + b
       const int in = M.size[Lh];
-      const double* w = M.theta + M.woff[Lh];
-      const double* b = M.theta + M.boff[Lh];
+      const double* w = theta + M.woff[Lh];
+      const double* b = theta + M.boff[Lh];
       const double* Bs = act + (Lh - 1) * Hp * 8;
       const int KS = mlp_round_up(in, 4) >> 2, MT = mlp_round_up(n, 8) >> 3;
       for (int mt = warp; mt < MT; mt += nwarp) {
@@ -284,7 +285,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const ZView
         double c0 = o < n ? b[o] : 0.0, c1 = c0;
         _Pragma("unroll 4") for (int ks = 0; ks < KS; ++ks) {
           const int i = 4 * ks + t;
-          const double a = (i < in && o < n) ? __ldg(w + i * n + o) : 0.0;
+          const double a = (i < in && o < n) ? (*(w + i * n + o)) : 0.0;
           dmma_m8n8k4(c0, c1, a, Bs[i * 8 + g]);
         }
         if (o < n) {
@@ -299,7 +300,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const ZView
     if (MODE == 2) {
       for (int j = Lh; j >= 1; --j) {
         const int rows = M.size[j], k = M.size[j + 1];
-        const double* w = M.theta + M.woff[j];
+        const double* w = theta + M.woff[j];
         const double* Bs = j == Lh ? mub : zb + ((j + 1) & 1) * Hp * 8;
         const int KS = mlp_round_up(k, 4) >> 2, MT = mlp_round_up(rows, 8) >> 3;
         for (int mt = warp; mt < MT; mt += nwarp) {
@@ -307,7 +308,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const ZView
           double c0 = 0.0, c1 = 0.0;
           _Pragma("unroll 4") for (int ks = 0; ks < KS; ++ks) {
             const int o = 4 * ks + t;
-            const double a = (i < rows && o < k) ? __ldg(w + i * k + o) : 0.0;
+            const double a = (i < rows && o < k) ? (*(w + i * k + o)) : 0.0;
             dmma_m8n8k4(c0, c1, a, Bs[o * 8 + g]);
           }
           const int pos = i * 8 + 2 * t;
@@ -329,7 +330,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const ZView
     }
     for (int j = 0; j < Lh; ++j) {
       const int in = M.size[j], out = M.size[j + 1];
-      const double* w = M.theta + M.woff[j];
+      const double* w = theta + M.woff[j];
       const int KS = mlp_round_up(in, 4) >> 2, MT = mlp_round_up(out, 8) >> 3;
       double c[kRounds][NW][2];
 #pragma unroll
@@ -339,13 +340,13 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const ZView
           const int o = 8 * mt + g;
           if (j == 0) {
 #pragma unroll
-            for (int i = 0; i < NW; ++i) { const double v = o < out ? __ldg(w + i * out + o) : 0.0; c[r][i][0] = v; c[r][i][1] = v; }
+            for (int i = 0; i < NW; ++i) { const double v = o < out ? (*(w + i * out + o)) : 0.0; c[r][i][0] = v; c[r][i][1] = v; }
           } else {
 #pragma unroll
             for (int i = 0; i < NW; ++i) { c[r][i][0] = 0.0; c[r][i][1] = 0.0; }
             _Pragma("unroll 4") for (int ks = 0; ks < KS; ++ks) {
               const int k = 4 * ks + t;
-              const double a = (k < in && o < out) ? __ldg(w + k * out + o) : 0.0;
+              const double a = (k < in && o < out) ? (*(w + k * out + o)) : 0.0;
 #pragma unroll
               for (int i = 0; i < NW; ++i) dmma_m8n8k4(c[r][i][0], c[r][i][1], a, tb[i * Hp * 8 + k * 8 + g]);
             }
@@ -382,7 +383,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const ZView
     }
     {  // Jacobian rows: ydot_i = W_Lh^T (d h_Lh / d v_i)
       const int in = M.size[Lh];
-      const double* w = M.theta + M.woff[Lh];
+      const double* w = theta + M.woff[Lh];
       const int KS = mlp_round_up(in, 4) >> 2, MT = mlp_round_up(n, 8) >> 3;
       for (int mt = warp; mt < MT; mt += nwarp) {
         const int o = 8 * mt + g;
@@ -391,7 +392,7 @@ __device__ __noinline__ void mlp_nodes_pass(const Problem& P, int Q, const ZView
         for (int i = 0; i < NW; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
         _Pragma("unroll 4") for (int ks = 0; ks < KS; ++ks) {
           const int k = 4 * ks + t;
-          const double a = (k < in && o < n) ? __ldg(w + k * n + o) : 0.0;
+          const double a = (k < in && o < n) ? (*(w + k * n + o)) : 0.0;
 #pragma unroll
           for (int i = 0; i < NW; ++i) dmma_m8n8k4(c[i][0], c[i][1], a, tb[i * Hp * 8 + k * 8 + g]);
         }
