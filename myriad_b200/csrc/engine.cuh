@@ -63,7 +63,7 @@ template <class S>
 struct Dims {
   static constexpr int NW = S::NW, NC = S::NC, NWP = S::NWP;
   static constexpr int GS = pad2(NC * NW);   // Jacobian block of a node role
-  static constexpr int HS = pad2(NW * NW);   // node-block inverse (full)
+  static constexpr int HS = pad2(NWP);       // node-block inverse (symmetric: packed upper triangle)
   static constexpr int WSZ = pad2(NWP);      // packed Hessian block
   static constexpr int BS = pad2(NC * NC);   // Schur-complement block
 };
@@ -129,6 +129,7 @@ struct WS {
   double* mlp_scr;   // NODE systems: scratch of the cooperative MLP pass (shared memory), else null
   const double* theta;   // NODE systems: shared-memory copy of the MLP weights (null: read the caller's vector)
   int vq0, vi0, vqs, vis;   // VarIter: start (node, component) of this thread and its stride
+  int sh;                   // 0: nothing assumed; 1: CR scratch in shared memory; 2: also Hinv, G, F (MYR_ASSUME_SHARED)
   MYR_HDI WS(const L& lay, unsigned long long mask, double* smem, double* glob) {
     Q = lay.Q; St = lay.St; ldq = lay.ldq;
     vi0 = MYR_TID / Q; vq0 = MYR_TID - vi0 * Q; vis = MYR_NT / Q; vqs = MYR_NT - vis * Q;
@@ -136,7 +137,7 @@ struct WS {
 #define X(name, sz) if ((mask >> L::A_##name) & 1ull) { name = sp; sp += lay.size[L::A_##name]; } else { name = gp; gp += lay.size[L::A_##name]; }
     MYR_WS_ARRAYS(X)
 #undef X
-    red = nullptr; mlp_scr = nullptr; theta = nullptr;
+    red = nullptr; mlp_scr = nullptr; theta = nullptr; sh = 0;
   }
   MYR_HDI uint32_t* fix() const { return reinterpret_cast<uint32_t*>(fixm); }
 };
@@ -155,6 +156,17 @@ struct VarIter {
   }
 };
 #define MYR_FOR_VARS(it) for (VarIter<S> it(ws); it.valid(); it.next(ws))
+
+// Address-space hints.  The slot's arrays are reached through generic pointers (an array may live in shared OR global
+// memory, Layout::place decides at run time); a generic load from shared memory goes through the global-load path --
+// long-scoreboard latency, 64-bit addressing.  The hot routines are therefore compiled in variants that ASSUME their
+// matrices are in shared memory (SH = 1: the cyclic-reduction scratch; SH = 2: also Hinv / G / F) and the kernel
+// picks the variant that matches the placement mask; nvcc then emits LDS / STS for them.
+#ifdef __CUDA_ARCH__
+#define MYR_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define MYR_ASSUME_SHARED(p) ((void)0)
+#endif
 
 #define NQ(arr, q, e) ws.arr[(e) * ws.ldq + (q)]
 #define NS(arr, j, r) ws.arr[(j) * NC + (r)]
@@ -480,9 +492,10 @@ __device__ __forceinline__ void coop_inverse(double (&a)[N], int r, bool& ok, in
 }
 #endif
 
-template <int NC>
+template <int NC, int SH = 0>
 MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU, double* b, double* x,
                             int& cp, int& cn, int& cz) {
+  if (SH >= 1) { MYR_ASSUME_SHARED(D); MYR_ASSUME_SHARED(U); MYR_ASSUME_SHARED(VL); MYR_ASSUME_SHARED(VU); MYR_ASSUME_SHARED(b); MYR_ASSUME_SHARED(x); }
   constexpr int BB = NC * NC;
   constexpr int BS = pad2(BB);
   constexpr int G = CrGroup<NC>::G;
@@ -511,9 +524,9 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
       // every lane inverts the whole (small) block redundantly: no cross-lane traffic, and lane rl keeps row rl
       double M[BB], X[BB];
 #pragma unroll
-      for (int e = 0; e < BB; ++e) M[e] = Di[e];
+      for (int e = 0; e < BB; ++e) M[e] = active ? Di[e] : ((e % (NC + 1)) == 0 ? 1.0 : 0.0);   // idle groups invert the identity
       small_sym_inverse<NC>(M, X, ok, p_, n_);
-      ok = ok || !active;
+      __syncwarp();   // every lane of the group has read ALL rows of D_i before any lane overwrites its row below
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         double v = 0.0;
@@ -806,15 +819,17 @@ MYR_HDN void block_cr_resolve(int St, const double* D, const double* VL, const d
 }
 
 // J_q^T d for the two roles of node q:  u[i] = sum_r G[r][i] dp[r] + F[r][i] ds[r]
-template <class S>
+template <class S, int SH = 0>
 MYR_HDI void jt_times(const Problem& P, const WS<S>& ws, int q, const double* dvec /* stage-major */, double* u) {
   using D = Dims<S>;
   constexpr int NW = S::NW, NC = S::NC;
+  const double* const Gb = ws.G; const double* const Fb = ws.F;
+  if (SH >= 2) { MYR_ASSUME_SHARED(Gb); MYR_ASSUME_SHARED(Fb); }
 #pragma unroll
   for (int i = 0; i < NW; ++i) u[i] = 0.0;
   const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
   if (jp >= 0) {
-    const double* Gq = ws.G + q * D::GS;
+    const double* Gq = Gb + q * D::GS;
 #pragma unroll
     for (int r = 0; r < NC; ++r) {
       const double d = dvec[jp * NC + r];
@@ -823,7 +838,7 @@ MYR_HDI void jt_times(const Problem& P, const WS<S>& ws, int q, const double* dv
     }
   }
   if (js >= 0) {
-    const double* Fq = ws.F + q * D::GS;
+    const double* Fq = Fb + q * D::GS;
 #pragma unroll
     for (int r = 0; r < NC; ++r) {
       const double d = dvec[js * NC + r];
@@ -843,12 +858,16 @@ MYR_HDI void jt_times(const Problem& P, const WS<S>& ws, int q, const double* dv
 //   (2) per stage: sum the role products of the stage's nodes into the Schur-complement block, right-hand side;
 //   (3) block cyclic reduction -> dlam, inertia of S.
 // Returns the inertia-ok flag; minpr = smallest relative pivot of the node blocks (refinement is only worth it when small).
-template <class S>
+template <class S, int SH = 0>
 MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, double delta_c, double delta_reg, double& minpr_out,
                         int& parity) {
   using D = Dims<S>;
   constexpr int NW = S::NW, NC = S::NC, BS = D::BS;
   const int Q = ws.Q, St = ws.St;
+  double* const crD = ws.crD; double* const crU = ws.crU; double* const crVL = ws.crVL; double* const crVU = ws.crVU;
+  double* const crb = ws.crb; double* const Hb = ws.Hinv; const double* const Gb = ws.G; const double* const Fb = ws.F;
+  if (SH >= 1) { MYR_ASSUME_SHARED(crD); MYR_ASSUME_SHARED(crU); MYR_ASSUME_SHARED(crVL); MYR_ASSUME_SHARED(crVU); MYR_ASSUME_SHARED(crb); }
+  if (SH >= 2) { MYR_ASSUME_SHARED(Hb); MYR_ASSUME_SHARED(Gb); MYR_ASSUME_SHARED(Fb); }
 #if defined(MYR_PROFILE_PHASES) && defined(__CUDA_ARCH__)
   long long kph_t0_ = clock64();
 #define MYR_KPH(idx) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase_cycles[idx], (unsigned long long)(t_ - kph_t0_)); kph_t0_ = t_; } } while (0)
@@ -856,8 +875,8 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
 #define MYR_KPH(idx) do { } while (0)
 #endif
   // role-product slots: the k-th node block of a stage (phi_slot / psi_slot) writes into its own scratch
-  double* const slotM[3] = {ws.crD, ws.crVL, ws.crVU};
-  double* const slotV[3] = {ws.crb, ws.ct, ws.dl2};
+  double* const slotM[3] = {crD, crVL, crVU};
+  double* const slotV[3] = {crb, ws.ct, ws.dl2};
   int hn = 0, hz = 0;
   double minpr = INFINITY;
   for (int q = MYR_TID; q < Q; q += MYR_NT) {
@@ -874,9 +893,11 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
     sym_inverse<NW>(A, ws.fix()[q], inv, p_, n_, z_, &pr_);
     minpr = fmin(minpr, pr_);
     hn += n_; hz += z_;
-    double* Hq = ws.Hinv + q * D::HS;
+    double* Hq = Hb + q * D::HS;
 #pragma unroll
-    for (int i = 0; i < NW * NW; ++i) Hq[i] = inv[i];
+    for (int i = 0; i < NW; ++i)
+#pragma unroll
+      for (int j = i; j < NW; ++j) Hq[pidx(i, j, NW)] = inv[i * NW + j];
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
       double a = 0.0;
@@ -886,8 +907,8 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
       NQ(tv, q, i) = a;
     }
     const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-    const double* Gq = ws.G + q * D::GS;
-    const double* Fq = ws.F + q * D::GS;
+    const double* Gq = Gb + q * D::GS;
+    const double* Fq = Fb + q * D::GS;
     if (jp >= 0) {
       const int sl = S::phi_slot(P, q);
       double* Dst = slotM[sl] + jp * BS;
@@ -919,7 +940,7 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
       const int sl = S::psi_slot(P, q);
       double* Dst = slotM[sl] + js * BS;
       double* vst = slotV[sl] + js * NC;
-      double* Ust = ws.crU + js * BS;
+      double* Ust = crU + js * BS;
       const bool link = jp >= 0;   // the node also starts the next stage: coupling block U_js = F Hinv G^T
 #pragma unroll
       for (int r = 0; r < NC; ++r) {
@@ -972,18 +993,18 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
 #pragma unroll
       for (int r = 0; r < NC; ++r) bj[r] -= vs[r];
     }
-    double* Dd = ws.crD + j * BS;
+    double* Dd = crD + j * BS;
 #pragma unroll
     for (int r = 0; r < NC; ++r)
 #pragma unroll
       for (int c2 = 0; c2 < NC; ++c2) Dd[r * NC + c2] = 0.5 * (Dj[r * NC + c2] + Dj[c2 * NC + r]) + (r == c2 ? delta_c : 0.0);
 #pragma unroll
-    for (int r = 0; r < NC; ++r) { ws.crb[j * NC + r] = bj[r]; NS(sch, j, r) = bj[r] - NS(c, j, r); }
+    for (int r = 0; r < NC; ++r) { crb[j * NC + r] = bj[r]; NS(sch, j, r) = bj[r] - NS(c, j, r); }
   }
   MYR_SYNC();
   MYR_KPH(7);
   int sp, sn, sz;
-  block_cr_solve<NC>(St, ws.crD, ws.crU, ws.crVL, ws.crVU, ws.crb, ws.dlam, sp, sn, sz);
+  block_cr_solve<NC, SH>(St, crD, crU, crVL, crVU, crb, ws.dlam, sp, sn, sz);
   MYR_KPH(8);
   double rv[5] = {(double)hn, (double)hz, minpr, (double)sn, (double)sz};
   block_reduce_multi<R_SUM, R_SUM, R_MIN, R_SUM, R_SUM>(rv, ws.red, parity);
@@ -995,20 +1016,23 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
 
 // dz = -(tv + Hinv J^T dl) for the multiplier step dl (stage-major), tv = Hinv rb; written to the node vector dst.
 // Returns this thread's part of  dz^T H dz = -dz . (rb + J^T dl)  (H dz = -(rb + J^T dl) on the free variables).
-template <class S>
+template <class S, int SH = 0>
 MYR_HDI double kkt_backsub(const Problem& P, const WS<S>& ws, const double* dl, double* dst) {
   using D = Dims<S>;
   constexpr int NW = S::NW;
+  const double* const Hb = ws.Hinv;
+  if (SH >= 2) MYR_ASSUME_SHARED(Hb);
+  if (SH >= 1) MYR_ASSUME_SHARED(dl);   // dlam / dl2... only dlam belongs to the CR group: callers pass SH accordingly
   double dHd = 0.0;
   for (int q = MYR_TID; q < ws.Q; q += MYR_NT) {
     double u[NW];
-    jt_times<S>(P, ws, q, dl, u);
-    const double* Hq = ws.Hinv + q * D::HS;
+    jt_times<S, SH>(P, ws, q, dl, u);
+    const double* Hq = Hb + q * D::HS;
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
       double a = NQ(tv, q, i);
 #pragma unroll
-      for (int k = 0; k < NW; ++k) a += Hq[i * NW + k] * u[k];
+      for (int k = 0; k < NW; ++k) a += Hq[pidx(i, k, NW)] * u[k];
       dst[i * ws.ldq + q] = -a;
       dHd += a * (NQ(rb, q, i) + u[i]);   // a = -dz_i (zero on fixed variables: their rows of Hinv vanish)
     }
@@ -1067,7 +1091,7 @@ MYR_HDI void kkt_refine(const Problem& P, const WS<S>& ws, double delta_w, doubl
         for (int i = 0; i < NW; ++i) {
           double a = 0.0;
 #pragma unroll
-          for (int k2 = 0; k2 < NW; ++k2) a += Hq[i * NW + k2] * NQ(dzL, q, k2);
+          for (int k2 = 0; k2 < NW; ++k2) a += Hq[pidx(i, k2, NW)] * NQ(dzL, q, k2);
           t[i] = a;
         }
 #pragma unroll
@@ -1100,7 +1124,7 @@ MYR_HDI void kkt_refine(const Problem& P, const WS<S>& ws, double delta_w, doubl
       for (int i = 0; i < NW; ++i) {
         double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < NW; ++k) a += Hq[i * NW + k] * v[k];
+        for (int k = 0; k < NW; ++k) a += Hq[pidx(i, k, NW)] * v[k];
         NQ(dz, q, i) += a;
       }
     }
@@ -1109,13 +1133,13 @@ MYR_HDI void kkt_refine(const Problem& P, const WS<S>& ws, double delta_w, doubl
 }
 
 // complete KKT solve (factor, multipliers, primal step, optional refinement): what myr_kkt_solve exposes
-template <class S>
+template <class S, int SH = 0>
 MYR_HDI bool kkt_solve(const Problem& P, const WS<S>& ws, double delta_w, double delta_c, double delta_reg, int max_refine, int& parity,
                        double* dHd_part = nullptr) {
   double minpr;
-  const bool ok = kkt_factor<S>(P, ws, delta_w, delta_c, delta_reg, minpr, parity);
+  const bool ok = kkt_factor<S, SH>(P, ws, delta_w, delta_c, delta_reg, minpr, parity);
   if (!ok) return false;
-  const double dHd = kkt_backsub<S>(P, ws, ws.dlam, ws.dz);
+  const double dHd = kkt_backsub<S, SH>(P, ws, ws.dlam, ws.dz);
   if (dHd_part) *dHd_part = dHd;
   MYR_SYNC();
   // refinement is only worth its cost when some node block was close to singular
@@ -1281,7 +1305,16 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     bool ok = false;
     for (int tries = 0; tries < 60; ++tries) {
       // accurate steps only matter near the solution: refine the linear solve in the end game only
-      ok = kkt_solve<S>(P, ws, delta, O.delta_c, O.delta_reg, E0 < 1e-3 ? O.max_refine : 0, parity, &dHd);
+      const int refine = E0 < 1e-3 ? O.max_refine : 0;
+#if defined(__CUDA_ARCH__) && defined(MYR_FORCE_SH)
+      ok = kkt_solve<S, MYR_FORCE_SH>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd);   // experiment: one variant only
+#elif defined(__CUDA_ARCH__) && defined(MYR_DISPATCH_SH)
+      if (ws.sh == 2) ok = kkt_solve<S, 2>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd);
+      else if (ws.sh == 1) ok = kkt_solve<S, 1>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd);
+      else ok = kkt_solve<S, 0>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd);
+#else
+      ok = kkt_solve<S, 0>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd);
+#endif
       if (ok) break;
       if (delta == 0.0) delta = (delta_last == 0.0) ? O.delta_0 : fmax(O.delta_min, O.kappa_w_minus * delta_last);
       else delta *= (delta_last == 0.0) ? O.kappa_w_plus_first : O.kappa_w_plus;

@@ -689,7 +689,12 @@ inline IpmOpts make_opts(const MyrIpmOpts* o) {
   r.eta = 1e-4; r.rho = 0.1;
   r.delta_reg = 1e-8; r.max_refine = 1;
   r.max_soc = (o && o->max_soc != 0) ? (o->max_soc > 0 ? o->max_soc : 0) : 4;
-  if (const char* e = getenv("MYR_DELTA_REG")) r.delta_reg = atof(e);      // tuning knobs (debug)
+  if (const char* e = getenv("MYR_MU_INIT")) r.mu_init = atof(e);          // tuning knobs (debug)
+  if (const char* e = getenv("MYR_KAPPA_MU")) r.kappa_mu = atof(e);
+  if (const char* e = getenv("MYR_THETA_MU")) r.theta_mu = atof(e);
+  if (const char* e = getenv("MYR_KAPPA_EPS")) r.kappa_eps = atof(e);
+  if (const char* e = getenv("MYR_TAU_MIN")) r.tau_min = atof(e);
+  if (const char* e = getenv("MYR_DELTA_REG")) r.delta_reg = atof(e);
   if (const char* e = getenv("MYR_MAX_REFINE")) r.max_refine = atoi(e);
   if (const char* e = getenv("MYR_MAX_SOC")) r.max_soc = atoi(e) > 0 ? atoi(e) : 0;
   return r;
@@ -707,6 +712,12 @@ ipm_kernel(Problem P, IpmOpts O, IpmIO io, unsigned long long mask, int smem_dou
   WS<S> ws(L, mask, smem + 2 * kRedStride, work + (long long)blockIdx.x * slot_stride);
   ws.red = smem;
   ws.mlp_scr = smem + 2 * kRedStride + smem_doubles + theta_doubles;
+  {
+    using LY = Layout<S>;
+    const unsigned long long cr = (1ull << LY::kCrArrays) - 1ull;
+    const unsigned long long nodem = (1ull << LY::A_Hinv) | (1ull << LY::A_G) | (1ull << LY::A_F);
+    ws.sh = (mask & cr) == cr ? (((mask & nodem) == nodem) ? 2 : 1) : 0;
+  }
   if (Layout<S>::kCoopMlp) {   // weights into shared memory once per (persistent) CTA
     double* th = smem + 2 * kRedStride + smem_doubles;
     for (int e = threadIdx.x; e < theta_doubles; e += blockDim.x) th[e] = e < P.mlp.boff[P.mlp.L - 1] + P.mlp.size[P.mlp.L] ? P.mlp.theta[e] : 0.0;
