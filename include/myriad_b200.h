@@ -65,8 +65,12 @@ enum {
   /* NodeSystem (myriad/systems/neural_ode/node_system.py:14-42) wrapping true system k: id = MYR_SYS_NODE_BASE + k.
    * Dynamics = the NODE MLP of myriad/neural_ode/create_node.py:110-117 (weights in MyrDesc.theta); cost, bounds,
    * horizon and the verification rollout are the true system's. */
-  MYR_SYS_NODE_BASE = 100
+  MYR_SYS_NODE_BASE = 100,
+  /* systems registered at run time with myr_register_system (the reference's "add a SystemType member" plugin point,
+   * myriad/systems/__init__.py:29-50): ids from MYR_SYS_USER_BASE up */
+  MYR_SYS_USER_BASE = 1000
 };
+#define MYR_MAX_USER_SYSTEMS 64
 /* OptimizerType x QuadratureRule (myriad/config.py:12-17,53-56; get_optimizer, trajectory_optimizers/__init__.py:12-28) */
 enum { MYR_OPT_SHOOTING = 0, MYR_OPT_TRAPEZOIDAL = 1, MYR_OPT_HERMITE_SIMPSON = 2 };
 /* IntegrationMethod (myriad/config.py:46-50) */
@@ -193,6 +197,12 @@ int myr_dynamics(const MyrDesc* desc, int B, const double* x, const double* u, c
  * the vector-Jacobian product the reference takes with jax.grad of the Lagrangian in its extragradient solver
  * (myriad/nlp_solvers/extra_gradient.py:21-33).  Works for all three transcriptions. */
 int myr_jtvec(const MyrDesc* desc, int B, const double* Jblk, const double* lam, double* out, void* stream);
+
+/* Registers a system that was compiled into its own shared library (myriad_b200/plugin.py builds it from symbolic
+ * dynamics / cost with the same generator and kernel templates as the built-in systems).  vtable: the pointer returned by
+ * the plugin library's myr_vtable_<Sys>() export; its id must be >= MYR_SYS_USER_BASE.  Replaces subclassing
+ * FiniteHorizonControlSystem + adding a SystemType member (myriad/systems/base.py:11-111, systems/__init__.py:29-50). */
+int myr_register_system(const void* vtable);
 
 /* Measurement helper (no reference counterpart): launches `blocks` CTAs x 1024 threads, each doing `iters` rounds of 8
  * independent fp64 FMAs (2 * 8 * iters * 1024 * blocks flops); out: [blocks * 1024] doubles.  bench.py times it with

@@ -59,7 +59,7 @@ _P = C.c_void_p
 _lib = None
 
 EXPORTS = ["myr_abi_version", "myr_last_error", "myr_problem_sizes", "myr_eval", "myr_kkt_solve", "myr_ipm_solve",
-           "myr_rollout_cost", "myr_dynamics", "myr_jtvec", "myr_bench_dfma", "myr_host_eval", "myr_host_kkt_solve", "myr_host_ipm_solve",
+           "myr_rollout_cost", "myr_dynamics", "myr_jtvec", "myr_register_system", "myr_bench_dfma", "myr_host_eval", "myr_host_kkt_solve", "myr_host_ipm_solve",
            "myr_host_rollout_cost", "myr_host_dynamics", "myr_host_jtvec"]
 
 
@@ -70,7 +70,7 @@ def lib() -> C.CDLL:
   if not os.path.exists(LIB_PATH):
     raise MyriadError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(nvcc, sm_100a).  myriad_b200 has no CPU fallback.")
-  L = C.CDLL(LIB_PATH)
+  L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)   # plugin libraries (register_system) resolve myr::fail etc. against it
   L.myr_abi_version.restype = C.c_int
   L.myr_last_error.restype = C.c_char_p
   L.myr_problem_sizes.argtypes = [C.POINTER(MyrDesc), C.POINTER(MyrSizes)]
@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
   jt = [C.POINTER(MyrDesc), C.c_int, _P, _P, _P]
   L.myr_jtvec.argtypes = jt + [_P]
   L.myr_host_jtvec.argtypes = jt
+  L.myr_register_system.argtypes = [_P]
   L.myr_bench_dfma.argtypes = [C.c_int, C.c_int, _P, _P]
   for name in EXPORTS:
     if name not in ("myr_abi_version", "myr_last_error"):
@@ -108,6 +109,9 @@ def check(rc: int) -> None:
     if rc == -2:
       raise NotImplementedError(msg)
     raise MyriadError(f"myriad_b200 error {rc}: {msg}")
+
+
+USER_BASE = 1000  # MYR_SYS_USER_BASE
 
 
 def make_desc(system: str, optimizer: int, method: str, intervals: int, cpi: int = 1, T: float = 0.0, params=None,

@@ -62,7 +62,24 @@ MYR_BUILD_SYSTEMS(MYR_DECL)
 MYR_BUILD_NODE_SYSTEMS(MYR_DECL)
 #undef MYR_DECL
 
+// systems registered at run time (myr_register_system): one extra shared library per user-defined system, built by
+// myriad_b200/plugin.py from the same generator and the same kernel templates as the built-in ones
+static const SysVTable* g_user_systems[MYR_MAX_USER_SYSTEMS];
+static int g_num_user_systems = 0;
+
+extern "C" int myr_register_system(const void* vtable) {
+  const SysVTable* vt = static_cast<const SysVTable*>(vtable);
+  if (!vt || vt->id < MYR_SYS_USER_BASE) return fail(MYR_E_BADARG, "user systems need an id >= MYR_SYS_USER_BASE (got %s%lld)", "", vt ? vt->id : -1);
+  for (int i = 0; i < g_num_user_systems; ++i)
+    if (g_user_systems[i]->id == vt->id) { g_user_systems[i] = vt; return MYR_OK; }
+  if (g_num_user_systems >= MYR_MAX_USER_SYSTEMS) return fail(MYR_E_UNSUPPORTED, "too many registered systems%s", "", 0);
+  g_user_systems[g_num_user_systems++] = vt;
+  return MYR_OK;
+}
+
 static const SysVTable* find_system(int id) {
+  for (int i = 0; i < g_num_user_systems; ++i)
+    if (g_user_systems[i]->id == id) return g_user_systems[i];
 #define MYR_TRY(SYS) if (SYS::id == id) return myr_vtable_##SYS();
   MYR_BUILD_SYSTEMS(MYR_TRY)
 #undef MYR_TRY

@@ -11,6 +11,9 @@
 #pragma nv_diag_suppress 550
 
 #include "systems_gen.cuh"
+#ifdef MYR_EXTRA_SYSTEM_HEADER   // a user-defined system (myriad_b200/plugin.py): generated the same way, compiled on its own
+#include MYR_EXTRA_SYSTEM_HEADER
+#endif
 
 namespace myr {
 

@@ -44,6 +44,14 @@ struct scheme_is_lifted { static constexpr bool value = false; };
 template <class S>
 struct scheme_is_lifted<S, typename std::enable_if<S::kLifted>::type> { static constexpr bool value = true; };
 
+// collocation schemes whose role Jacobians are affine in the dynamics Jacobian (schemes.cuh, kAffineJ): the slot stores
+// J (n x NW per node) instead of G and F, and every product with a role Jacobian is formed from J and the role's
+// coefficients -- half the shared memory and less than half the flops of the per-node phase
+template <class S, class = void>
+struct scheme_is_affine { static constexpr bool value = false; };
+template <class S>
+struct scheme_is_affine<S, typename std::enable_if<S::kAffineJ>::type> { static constexpr bool value = true; };
+
 // ------------------------------------------------------------------ optional per-phase cycle accounting (debug builds)
 // -DMYR_PROFILE_PHASES: thread 0 of every CTA accumulates clock64() deltas per phase into g_phase_cycles (read back
 // with myr_debug_phase_cycles); compiled out of the product build.
@@ -62,7 +70,8 @@ MYR_HDI constexpr int pad2(int n) { return ((n + 1) & ~3) + 2; }
 template <class S>
 struct Dims {
   static constexpr int NW = S::NW, NC = S::NC, NWP = S::NWP;
-  static constexpr int GS = pad2(NC * NW);   // Jacobian block of a node role
+  static constexpr bool kAff = scheme_is_affine<S>::value;
+  static constexpr int GS = kAff ? pad2(S::n * NW) : pad2(NC * NW);   // Jacobian block of a node role (affine schemes: J itself)
   static constexpr int HS = pad2(NWP);       // node-block inverse (symmetric: packed upper triangle)
   static constexpr int WSZ = pad2(NWP);      // packed Hessian block
   static constexpr int BS = pad2(NC * NC);   // Schur-complement block
@@ -71,7 +80,7 @@ struct Dims {
 // X(name, doubles): in shared-memory PRIORITY order
 #define MYR_WS_ARRAYS(X)                                                                                              \
   X(crD, St * D::BS) X(crU, St * D::BS) X(crVL, St * D::BS) X(crVU, St * D::BS) X(crb, St * NC) X(dlam, St * NC)       \
-  X(Hinv, Q * D::HS) X(G, Q * D::GS) X(F, Q * D::GS)                                                                  \
+  X(Hinv, Q * D::HS) X(G, Q * D::GS) X(F, D::kAff ? 0 : Q * D::GS)                                                                  \
   X(dynf, kCoopMlp ? Q * S::n : 0) X(dynJ, kCoopMlp ? Q * S::n * NW : 0) X(dynH, kCoopMlp ? Q * S::NWP : 0)           \
   X(lam, St * NC) X(z, ldq * NW) X(rb, ldq * NW) X(dz, ldq * NW) X(tv, ldq * NW) X(fixm, (Q + 1) / 2)                   \
   X(W, Q * D::WSZ) X(gl, ldq * NW) X(zL, ldq * NW) X(zU, ldq * NW) X(lbr, ldq * NW) X(ubr, ldq * NW)                    \
@@ -258,6 +267,26 @@ struct WsZView {
   MYR_HDI double operator()(int q, int i) const { return z[i * ldq + q]; }
 };
 
+// ------------------------------------------------------------------ affine role Jacobians (scheme_is_affine)
+// w = sum_g a_p[g] dp_g + a_s[g] ds_g,  e = sum_g b_p[g] dp_g + b_s[g] ds_g   (dp / ds: the node's phi / psi stage rows of
+// a stage vector; null = role absent), so that  J_roles^T d = J^T w + [e; 0]
+template <class S>
+MYR_HDI void affine_combine(const Problem& P, int q, const double* dp, const double* ds, double* w, double* e) {
+  constexpr int n = S::n, NG = S::NG;
+  double ap[NG], bp[NG], as[NG], bs[NG];
+  S::role_coefs(P, q, ap, bp, as, bs);
+#pragma unroll
+  for (int r = 0; r < n; ++r) { w[r] = 0.0; e[r] = 0.0; }
+#pragma unroll
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int r = 0; r < n; ++r) {
+      const double p_ = dp ? dp[g * n + r] : 0.0, s_ = ds ? ds[g * n + r] : 0.0;
+      w[r] += ap[g] * p_ + as[g] * s_;
+      e[r] += bp[g] * p_ + bs[g] * s_;
+    }
+}
+
 // ------------------------------------------------------------------ K1: node evaluation sweep
 // Evaluates every node at the point zv (element-major node vector: the iterate or a trial point) and stores the node
 // arrays in the slot.  MODE as in schemes.cuh; MODE 2 also leaves  grad f + J^T lam  (zero on fixed variables) in rb.
@@ -289,30 +318,57 @@ MYR_HDI double eval_nodes(const Problem& P, const WS<S>& ws, const double* zv) {
         ls[r] = js >= 0 ? NS(lam, js, r) : 0.0;
       }
     }
-    double ell, gl[NW], phi[NC], psi[NC], G[NC * NW], F[NC * NW], W[S::NWP];
-    S::template eval_node<MODE>(P, q, v, lp, ls, ell, gl, phi, psi, G, F, W, pre);
+    double ell, gl[NW], phi[NC], psi[NC], W[S::NWP];
+    if constexpr (D::kAff) {
+      double J[S::n * NW];
+      S::template eval_node_j<MODE>(P, q, v, lp, ls, ell, gl, phi, psi, J, W, pre);
+      if (MODE >= 1) {
+        double* Jq = ws.G + q * D::GS;
+#pragma unroll
+        for (int i = 0; i < S::n * NW; ++i) Jq[i] = J[i];
+      }
+      if (MODE == 2) {
+        double w_[S::n], e_[S::n];
+        affine_combine<S>(P, q, jp >= 0 ? lp : nullptr, js >= 0 ? ls : nullptr, w_, e_);
+        const uint32_t fm = ws.fix()[q];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          double r = gl[i] + (i < S::n ? e_[i < S::n ? i : 0] : 0.0);
+#pragma unroll
+          for (int rr = 0; rr < S::n; ++rr) r += J[rr * NW + i] * w_[rr];
+          NQ(rb, q, i) = ((fm >> i) & 1u) ? 0.0 : r;
+        }
+      }
+    } else {
+      double G[NC * NW], F[NC * NW];
+      S::template eval_node<MODE>(P, q, v, lp, ls, ell, gl, phi, psi, G, F, W, pre);
+      if (MODE >= 1) {
+        double* Gq = ws.G + q * D::GS; double* Fq = ws.F + q * D::GS;
+#pragma unroll
+        for (int i = 0; i < NC * NW; ++i) { Gq[i] = G[i]; Fq[i] = F[i]; }
+      }
+      if (MODE == 2) {
+        const uint32_t fm = ws.fix()[q];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          double r = gl[i];
+#pragma unroll
+          for (int rr = 0; rr < NC; ++rr) r += G[rr * NW + i] * lp[rr] + F[rr * NW + i] * ls[rr];
+          NQ(rb, q, i) = ((fm >> i) & 1u) ? 0.0 : r;
+        }
+      }
+    }
     fsum += ell;
 #pragma unroll
     for (int r = 0; r < NC; ++r) { ws.phi[q * NC + r] = phi[r]; ws.psi[q * NC + r] = psi[r]; }
     if (MODE >= 1) {
 #pragma unroll
       for (int i = 0; i < NW; ++i) NQ(gl, q, i) = gl[i];
-      double* Gq = ws.G + q * D::GS; double* Fq = ws.F + q * D::GS;
-#pragma unroll
-      for (int i = 0; i < NC * NW; ++i) { Gq[i] = G[i]; Fq[i] = F[i]; }
     }
     if (MODE == 2) {
       double* Wq = ws.W + q * D::WSZ;
 #pragma unroll
       for (int i = 0; i < S::NWP; ++i) Wq[i] = W[i];
-      const uint32_t fm = ws.fix()[q];
-#pragma unroll
-      for (int i = 0; i < NW; ++i) {
-        double r = gl[i];
-#pragma unroll
-        for (int rr = 0; rr < NC; ++rr) r += G[rr * NW + i] * lp[rr] + F[rr * NW + i] * ls[rr];
-        NQ(rb, q, i) = ((fm >> i) & 1u) ? 0.0 : r;
-      }
     }
   }
   return fsum;
@@ -825,25 +881,39 @@ MYR_HDI void jt_times(const Problem& P, const WS<S>& ws, int q, const double* dv
   constexpr int NW = S::NW, NC = S::NC;
   const double* const Gb = ws.G; const double* const Fb = ws.F;
   if (SH >= 2) { MYR_ASSUME_SHARED(Gb); MYR_ASSUME_SHARED(Fb); }
-#pragma unroll
-  for (int i = 0; i < NW; ++i) u[i] = 0.0;
   const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-  if (jp >= 0) {
-    const double* Gq = Gb + q * D::GS;
+  if constexpr (D::kAff) {
+    double w_[S::n], e_[S::n];
+    affine_combine<S>(P, q, jp >= 0 ? dvec + jp * NC : nullptr, js >= 0 ? dvec + js * NC : nullptr, w_, e_);
+    const double* Jq = Gb + q * D::GS;
 #pragma unroll
-    for (int r = 0; r < NC; ++r) {
-      const double d = dvec[jp * NC + r];
+    for (int i = 0; i < NW; ++i) {
+      double a = i < S::n ? e_[i < S::n ? i : 0] : 0.0;
 #pragma unroll
-      for (int i = 0; i < NW; ++i) u[i] += Gq[r * NW + i] * d;
+      for (int r = 0; r < S::n; ++r) a += Jq[r * NW + i] * w_[r];
+      u[i] = a;
     }
-  }
-  if (js >= 0) {
-    const double* Fq = Fb + q * D::GS;
+    (void)Fb;
+  } else {
 #pragma unroll
-    for (int r = 0; r < NC; ++r) {
-      const double d = dvec[js * NC + r];
+    for (int i = 0; i < NW; ++i) u[i] = 0.0;
+    if (jp >= 0) {
+      const double* Gq = Gb + q * D::GS;
 #pragma unroll
-      for (int i = 0; i < NW; ++i) u[i] += Fq[r * NW + i] * d;
+      for (int r = 0; r < NC; ++r) {
+        const double d = dvec[jp * NC + r];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) u[i] += Gq[r * NW + i] * d;
+      }
+    }
+    if (js >= 0) {
+      const double* Fq = Fb + q * D::GS;
+#pragma unroll
+      for (int r = 0; r < NC; ++r) {
+        const double d = dvec[js * NC + r];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) u[i] += Fq[r * NW + i] * d;
+      }
     }
   }
 }
@@ -907,71 +977,143 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
       NQ(tv, q, i) = a;
     }
     const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-    const double* Gq = Gb + q * D::GS;
-    const double* Fq = Fb + q * D::GS;
-    if (jp >= 0) {
-      const int sl = S::phi_slot(P, q);
-      double* Dst = slotM[sl] + jp * BS;
-      double* vst = slotV[sl] + jp * NC;
+    if constexpr (D::kAff) {
+      // role Jacobians  a J + b [I 0]:  with  M = J Hinv,  N = M J^T,  Y = M[:, :n],  X = Hinv[:n, :n]
+      //   (a1 J + b1 E) Hinv (a2 J + b2 E)^T = a1 a2 N + a1 b2 Y + b1 a2 Y^T + b1 b2 X
+      constexpr int n = S::n, NG = S::NG;
+      const double* Jq = Gb + q * D::GS;
+      double M[n * NW], Nn[n * n], Jt[n];
 #pragma unroll
-      for (int r = 0; r < NC; ++r) {
-        double T[NW];
+      for (int r = 0; r < n; ++r) {
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
           double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < NW; ++k) a += Gq[r * NW + k] * inv[k * NW + i];
-          T[i] = a;
-        }
-#pragma unroll
-        for (int c2 = 0; c2 < NC; ++c2) {
-          double a = 0.0;
-#pragma unroll
-          for (int i = 0; i < NW; ++i) a += T[i] * Gq[c2 * NW + i];
-          Dst[r * NC + c2] = a;
+          for (int k = 0; k < NW; ++k) a += Jq[r * NW + k] * inv[k * NW + i];
+          M[r * NW + i] = a;
         }
         double a = 0.0;
 #pragma unroll
-        for (int i = 0; i < NW; ++i) a += Gq[r * NW + i] * t[i];
-        vst[r] = a;
+        for (int i = 0; i < NW; ++i) a += Jq[r * NW + i] * t[i];
+        Jt[r] = a;
       }
-    }
-    if (js >= 0) {
-      const int sl = S::psi_slot(P, q);
-      double* Dst = slotM[sl] + js * BS;
-      double* vst = slotV[sl] + js * NC;
-      double* Ust = crU + js * BS;
-      const bool link = jp >= 0;   // the node also starts the next stage: coupling block U_js = F Hinv G^T
 #pragma unroll
-      for (int r = 0; r < NC; ++r) {
-        double T[NW];
+      for (int r = 0; r < n; ++r)
 #pragma unroll
-        for (int i = 0; i < NW; ++i) {
+        for (int c2 = 0; c2 < n; ++c2) {
           double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < NW; ++k) a += Fq[r * NW + k] * inv[k * NW + i];
-          T[i] = a;
+          for (int i = 0; i < NW; ++i) a += M[r * NW + i] * Jq[c2 * NW + i];
+          Nn[r * n + c2] = a;
         }
+      double ap[NG], bp[NG], as[NG], bs[NG];
+      S::role_coefs(P, q, ap, bp, as, bs);
+      auto blk = [&](double a1, double b1, double a2, double b2, int r, int c2) {
+        return a1 * a2 * Nn[r * n + c2] + a1 * b2 * M[r * NW + c2] + b1 * a2 * M[c2 * NW + r] + b1 * b2 * inv[r * NW + c2];
+      };
+      if (jp >= 0) {
+        const int sl = S::phi_slot(P, q);
+        double* Dst = slotM[sl] + jp * BS;
+        double* vst = slotV[sl] + jp * NC;
 #pragma unroll
-        for (int c2 = 0; c2 < NC; ++c2) {
-          double a = 0.0;
+        for (int ga = 0; ga < NG; ++ga)
 #pragma unroll
-          for (int i = 0; i < NW; ++i) a += T[i] * Fq[c2 * NW + i];
-          Dst[r * NC + c2] = a;
-        }
-        if (link) {
+          for (int r = 0; r < n; ++r) {
 #pragma unroll
+            for (int gb = 0; gb < NG; ++gb)
+#pragma unroll
+              for (int c2 = 0; c2 < n; ++c2) Dst[(ga * n + r) * NC + gb * n + c2] = blk(ap[ga], bp[ga], ap[gb], bp[gb], r, c2);
+            vst[ga * n + r] = ap[ga] * Jt[r] + bp[ga] * t[r];
+          }
+      }
+      if (js >= 0) {
+        const int sl = S::psi_slot(P, q);
+        double* Dst = slotM[sl] + js * BS;
+        double* vst = slotV[sl] + js * NC;
+        double* Ust = crU + js * BS;
+        const bool link = jp >= 0;   // the node also starts the next stage: coupling block U_js = F Hinv G^T
+#pragma unroll
+        for (int ga = 0; ga < NG; ++ga)
+#pragma unroll
+          for (int r = 0; r < n; ++r) {
+#pragma unroll
+            for (int gb = 0; gb < NG; ++gb)
+#pragma unroll
+              for (int c2 = 0; c2 < n; ++c2) {
+                Dst[(ga * n + r) * NC + gb * n + c2] = blk(as[ga], bs[ga], as[gb], bs[gb], r, c2);
+                if (link) Ust[(ga * n + r) * NC + gb * n + c2] = blk(as[ga], bs[ga], ap[gb], bp[gb], r, c2);
+              }
+            vst[ga * n + r] = as[ga] * Jt[r] + bs[ga] * t[r];
+          }
+      }
+      (void)Fb;
+    } else {
+      const double* Gq = Gb + q * D::GS;
+      const double* Fq = Fb + q * D::GS;
+      if (jp >= 0) {
+        const int sl = S::phi_slot(P, q);
+        double* Dst = slotM[sl] + jp * BS;
+        double* vst = slotV[sl] + jp * NC;
+  #pragma unroll
+        for (int r = 0; r < NC; ++r) {
+          double T[NW];
+  #pragma unroll
+          for (int i = 0; i < NW; ++i) {
+            double a = 0.0;
+  #pragma unroll
+            for (int k = 0; k < NW; ++k) a += Gq[r * NW + k] * inv[k * NW + i];
+            T[i] = a;
+          }
+  #pragma unroll
           for (int c2 = 0; c2 < NC; ++c2) {
             double a = 0.0;
-#pragma unroll
+  #pragma unroll
             for (int i = 0; i < NW; ++i) a += T[i] * Gq[c2 * NW + i];
-            Ust[r * NC + c2] = a;
+            Dst[r * NC + c2] = a;
           }
+          double a = 0.0;
+  #pragma unroll
+          for (int i = 0; i < NW; ++i) a += Gq[r * NW + i] * t[i];
+          vst[r] = a;
         }
-        double a = 0.0;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) a += Fq[r * NW + i] * t[i];
-        vst[r] = a;
+      }
+      if (js >= 0) {
+        const int sl = S::psi_slot(P, q);
+        double* Dst = slotM[sl] + js * BS;
+        double* vst = slotV[sl] + js * NC;
+        double* Ust = crU + js * BS;
+        const bool link = jp >= 0;   // the node also starts the next stage: coupling block U_js = F Hinv G^T
+  #pragma unroll
+        for (int r = 0; r < NC; ++r) {
+          double T[NW];
+  #pragma unroll
+          for (int i = 0; i < NW; ++i) {
+            double a = 0.0;
+  #pragma unroll
+            for (int k = 0; k < NW; ++k) a += Fq[r * NW + k] * inv[k * NW + i];
+            T[i] = a;
+          }
+  #pragma unroll
+          for (int c2 = 0; c2 < NC; ++c2) {
+            double a = 0.0;
+  #pragma unroll
+            for (int i = 0; i < NW; ++i) a += T[i] * Fq[c2 * NW + i];
+            Dst[r * NC + c2] = a;
+          }
+          if (link) {
+  #pragma unroll
+            for (int c2 = 0; c2 < NC; ++c2) {
+              double a = 0.0;
+  #pragma unroll
+              for (int i = 0; i < NW; ++i) a += T[i] * Gq[c2 * NW + i];
+              Ust[r * NC + c2] = a;
+            }
+          }
+          double a = 0.0;
+  #pragma unroll
+          for (int i = 0; i < NW; ++i) a += Fq[r * NW + i] * t[i];
+          vst[r] = a;
+        }
       }
     }
   }
@@ -1084,7 +1226,6 @@ MYR_HDI void kkt_refine(const Problem& P, const WS<S>& ws, double delta_w, doubl
       const int nk = S::stage_nodes(P, j);
       for (int k = 0; k < nk; ++k) {
         int role; const int q = S::stage_node(P, j, k, role);
-        const double* Jq = (role ? ws.F : ws.G) + q * D::GS;
         const double* Hq = ws.Hinv + q * D::HS;
         double t[NW];
 #pragma unroll
@@ -1094,12 +1235,35 @@ MYR_HDI void kkt_refine(const Problem& P, const WS<S>& ws, double delta_w, doubl
           for (int k2 = 0; k2 < NW; ++k2) a += Hq[pidx(i, k2, NW)] * NQ(dzL, q, k2);
           t[i] = a;
         }
+        if constexpr (D::kAff) {
+          constexpr int n = S::n, NG = S::NG;
+          const double* Jq = ws.G + q * D::GS;
+          double ap[NG], bp[NG], as[NG], bs[NG], Jd[n], Jtt[n];
+          S::role_coefs(P, q, ap, bp, as, bs);
 #pragma unroll
-        for (int r = 0; r < NC; ++r) {
-          double a = 0.0, b_ = 0.0;
+          for (int r = 0; r < n; ++r) {
+            double a = 0.0, b_ = 0.0;
 #pragma unroll
-          for (int i = 0; i < NW; ++i) { a += Jq[r * NW + i] * NQ(dz, q, i); b_ += Jq[r * NW + i] * t[i]; }
-          rc[r] -= a; bj[r] += b_;
+            for (int i = 0; i < NW; ++i) { a += Jq[r * NW + i] * NQ(dz, q, i); b_ += Jq[r * NW + i] * t[i]; }
+            Jd[r] = a; Jtt[r] = b_;
+          }
+#pragma unroll
+          for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int r = 0; r < n; ++r) {
+              const double al = role ? as[g] : ap[g], be = role ? bs[g] : bp[g];
+              rc[g * n + r] -= al * Jd[r] + be * NQ(dz, q, r);
+              bj[g * n + r] += al * Jtt[r] + be * t[r];
+            }
+        } else {
+          const double* Jq = (role ? ws.F : ws.G) + q * D::GS;
+#pragma unroll
+          for (int r = 0; r < NC; ++r) {
+            double a = 0.0, b_ = 0.0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) { a += Jq[r * NW + i] * NQ(dz, q, i); b_ += Jq[r * NW + i] * t[i]; }
+            rc[r] -= a; bj[r] += b_;
+          }
         }
       }
 #pragma unroll

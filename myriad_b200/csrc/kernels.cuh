@@ -566,10 +566,27 @@ __host__ __device__ inline void kkt_instance(const Problem& P, int b, const doub
   const double* Jb = Jblk + (long long)b * jstride;
   for (int q = MYR_TID; q < ws.Q; q += MYR_NT) {
     const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
-    double* Gq = ws.G + q * D::GS; double* Fq = ws.F + q * D::GS; double* Wq = ws.W + q * D::WSZ;
-    for (int i = 0; i < NC * NW; ++i) {
-      Gq[i] = jp >= 0 ? Jb[((long long)jp * S::kMaxStageNodes + S::phi_slot(P, q)) * NC * NW + i] : 0.0;
-      Fq[i] = js >= 0 ? Jb[((long long)js * S::kMaxStageNodes + S::psi_slot(P, q)) * NC * NW + i] : 0.0;
+    double* Wq = ws.W + q * D::WSZ;
+    if constexpr (D::kAff) {
+      // the slot keeps the dynamics Jacobian J: recover it from the caller's role block  a J + b [I 0]  (Jblk as myr_eval
+      // returns it; row group with the largest |a| of whichever role the node has)
+      constexpr int n = S::n, NG = S::NG;
+      double ap[NG], bp[NG], as[NG], bs[NG];
+      S::role_coefs(P, q, ap, bp, as, bs);
+      const bool use_phi = jp >= 0;
+      const double* al = use_phi ? ap : as; const double* be = use_phi ? bp : bs;
+      int g = 0;
+      for (int k = 1; k < NG; ++k) if (fabs(al[k]) > fabs(al[g])) g = k;
+      const double* blk = Jb + ((long long)(use_phi ? jp : js) * S::kMaxStageNodes + (use_phi ? S::phi_slot(P, q) : S::psi_slot(P, q))) * NC * NW;
+      double* Jq = ws.G + q * D::GS;
+      for (int r = 0; r < n; ++r)
+        for (int i = 0; i < NW; ++i) Jq[r * NW + i] = (blk[(g * n + r) * NW + i] - (i == r ? be[g] : 0.0)) / al[g];
+    } else {
+      double* Gq = ws.G + q * D::GS; double* Fq = ws.F + q * D::GS;
+      for (int i = 0; i < NC * NW; ++i) {
+        Gq[i] = jp >= 0 ? Jb[((long long)jp * S::kMaxStageNodes + S::phi_slot(P, q)) * NC * NW + i] : 0.0;
+        Fq[i] = js >= 0 ? Jb[((long long)js * S::kMaxStageNodes + S::psi_slot(P, q)) * NC * NW + i] : 0.0;
+      }
     }
     for (int i = 0; i < S::NWP; ++i) Wq[i] = Hblk[((long long)b * ws.Q + q) * S::NWP + i];
     uint32_t fm = 0;

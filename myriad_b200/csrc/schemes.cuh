@@ -41,6 +41,16 @@ struct Trapezoid {
   static constexpr int n = Sys::n, m = Sys::m;
   static constexpr int NW = n + m, NC = n, NWP = NW * (NW + 1) / 2;
   static constexpr int kMaxStageNodes = 2;
+  // role Jacobians are affine in the dynamics Jacobian J (n x NW):  G = a_p J + b_p [I 0],  F = a_s J + b_s [I 0]  per
+  // row group (NG groups of n rows).  The interior-point kernel stores J once instead of G and F (engine.cuh).
+  static constexpr bool kAffineJ = true;
+  static constexpr int NG = 1;
+  MYR_HDI static void role_coefs(const Problem& P, int q, double* ap, double* bp, double* as, double* bs) {
+    const double hh = 0.5 * P.h;
+    const bool has_phi = q < P.N, has_psi = q >= 1;
+    ap[0] = has_phi ? hh : 0.0; bp[0] = has_phi ? 1.0 : 0.0;
+    as[0] = has_psi ? hh : 0.0; bs[0] = has_psi ? -1.0 : 0.0;
+  }
 
   MYR_HDI static int num_nodes(const Problem& P) { return P.N + 1; }
   MYR_HDI static int num_stages(const Problem& P) { return P.N; }
@@ -75,6 +85,19 @@ struct Trapezoid {
   MYR_HDI static void eval_node(const Problem& P, int q, const double* v, const double* lam_phi, const double* lam_psi,
                                 double& ell, double* gl, double* phi, double* psi, double* G, double* F, double* W,
                                 const PreDyn& pre = PreDyn()) {
+    eval_node_impl<MODE, false>(P, q, v, lam_phi, lam_psi, ell, gl, phi, psi, G, F, W, nullptr, pre);
+  }
+  // same, but returns the raw dynamics Jacobian J (n x NW) instead of the role Jacobians G, F
+  template <int MODE>
+  MYR_HDI static void eval_node_j(const Problem& P, int q, const double* v, const double* lam_phi, const double* lam_psi,
+                                  double& ell, double* gl, double* phi, double* psi, double* Jraw, double* W,
+                                  const PreDyn& pre = PreDyn()) {
+    eval_node_impl<MODE, true>(P, q, v, lam_phi, lam_psi, ell, gl, phi, psi, nullptr, nullptr, W, Jraw, pre);
+  }
+  template <int MODE, bool RAWJ>
+  MYR_HDI static void eval_node_impl(const Problem& P, int q, const double* v, const double* lam_phi, const double* lam_psi,
+                                     double& ell, double* gl, double* phi, double* psi, double* G, double* F, double* W,
+                                     double* Jraw, const PreDyn& pre) {
     const double h = P.h;
     const double hh = 0.5 * h;
     const bool has_phi = q < P.N, has_psi = q >= 1;
@@ -116,15 +139,20 @@ struct Trapezoid {
       }
 #pragma unroll
       for (int i = 0; i < NW; ++i) gl[i] *= wq;
+      if (RAWJ) {
 #pragma unroll
-      for (int r = 0; r < n; ++r)
+        for (int i = 0; i < n * NW; ++i) Jraw[i] = J[i];
+      } else {
 #pragma unroll
-        for (int i = 0; i < NW; ++i) {
-          const double a = hh * J[r * NW + i];
-          const double e = (i == r) ? 1.0 : 0.0;
-          G[r * NW + i] = has_phi ? a + e : 0.0;
-          F[r * NW + i] = has_psi ? a - e : 0.0;
-        }
+        for (int r = 0; r < n; ++r)
+#pragma unroll
+          for (int i = 0; i < NW; ++i) {
+            const double a = hh * J[r * NW + i];
+            const double e = (i == r) ? 1.0 : 0.0;
+            G[r * NW + i] = has_phi ? a + e : 0.0;
+            F[r * NW + i] = has_psi ? a - e : 0.0;
+          }
+      }
     }
 #pragma unroll
     for (int r = 0; r < n; ++r) {
@@ -150,6 +178,18 @@ struct HermiteSimpson {
   static constexpr int n = Sys::n, m = Sys::m;
   static constexpr int NW = n + m, NC = 2 * n, NWP = NW * (NW + 1) / 2;
   static constexpr int kMaxStageNodes = 3;
+  // row groups: 0 = defect rows, 1 = interpolation rows (see Trapezoid::kAffineJ)
+  static constexpr bool kAffineJ = true;
+  static constexpr int NG = 2;
+  MYR_HDI static void role_coefs(const Problem& P, int q, double* ap, double* bp, double* as, double* bs) {
+    const double h = P.h;
+    const bool mid = (q & 1);
+    const bool has_phi = q < 2 * P.N, has_psi = (!mid) && q >= 2;
+    ap[0] = has_phi ? (mid ? -4.0 * h / 6.0 : -h / 6.0) : 0.0; bp[0] = has_phi ? (mid ? 0.0 : -1.0) : 0.0;
+    ap[1] = has_phi ? (mid ? 0.0 : -h / 8.0) : 0.0;            bp[1] = has_phi ? (mid ? 1.0 : -0.5) : 0.0;
+    as[0] = has_psi ? -h / 6.0 : 0.0; bs[0] = has_psi ? 1.0 : 0.0;
+    as[1] = has_psi ? h / 8.0 : 0.0;  bs[1] = has_psi ? -0.5 : 0.0;
+  }
 
   MYR_HDI static int num_nodes(const Problem& P) { return 2 * P.N + 1; }
   MYR_HDI static int num_stages(const Problem& P) { return P.N; }
@@ -185,6 +225,19 @@ struct HermiteSimpson {
   MYR_HDI static void eval_node(const Problem& P, int q, const double* v, const double* lam_phi, const double* lam_psi,
                                 double& ell, double* gl, double* phi, double* psi, double* G, double* F, double* W,
                                 const PreDyn& pre = PreDyn()) {
+    eval_node_impl<MODE, false>(P, q, v, lam_phi, lam_psi, ell, gl, phi, psi, G, F, W, nullptr, pre);
+  }
+  // same, but returns the raw dynamics Jacobian J (n x NW) instead of the role Jacobians G, F
+  template <int MODE>
+  MYR_HDI static void eval_node_j(const Problem& P, int q, const double* v, const double* lam_phi, const double* lam_psi,
+                                  double& ell, double* gl, double* phi, double* psi, double* Jraw, double* W,
+                                  const PreDyn& pre = PreDyn()) {
+    eval_node_impl<MODE, true>(P, q, v, lam_phi, lam_psi, ell, gl, phi, psi, nullptr, nullptr, W, Jraw, pre);
+  }
+  template <int MODE, bool RAWJ>
+  MYR_HDI static void eval_node_impl(const Problem& P, int q, const double* v, const double* lam_phi, const double* lam_psi,
+                                     double& ell, double* gl, double* phi, double* psi, double* G, double* F, double* W,
+                                     double* Jraw, const PreDyn& pre) {
     const double h = P.h;
     const bool mid = (q & 1);
     const bool has_phi = q < 2 * P.N, has_psi = (!mid) && q >= 2;
@@ -239,17 +292,22 @@ struct HermiteSimpson {
       }
 #pragma unroll
       for (int i = 0; i < NW; ++i) gl[i] *= wq;
+      if (RAWJ) {
 #pragma unroll
-      for (int r = 0; r < n; ++r)
+        for (int i = 0; i < n * NW; ++i) Jraw[i] = J[i];
+      } else {
 #pragma unroll
-        for (int i = 0; i < NW; ++i) {
-          const double a = J[r * NW + i];
-          const double e = (i == r) ? 1.0 : 0.0;
-          G[r * NW + i] = has_phi ? cf_phi_d * a + cx_phi_d * e : 0.0;
-          G[(n + r) * NW + i] = has_phi ? cf_phi_i * a + cx_phi_i * e : 0.0;
-          F[r * NW + i] = has_psi ? cf_psi_d * a + cx_psi_d * e : 0.0;
-          F[(n + r) * NW + i] = has_psi ? cf_psi_i * a + cx_psi_i * e : 0.0;
-        }
+        for (int r = 0; r < n; ++r)
+#pragma unroll
+          for (int i = 0; i < NW; ++i) {
+            const double a = J[r * NW + i];
+            const double e = (i == r) ? 1.0 : 0.0;
+            G[r * NW + i] = has_phi ? cf_phi_d * a + cx_phi_d * e : 0.0;
+            G[(n + r) * NW + i] = has_phi ? cf_phi_i * a + cx_phi_i * e : 0.0;
+            F[r * NW + i] = has_psi ? cf_psi_d * a + cx_psi_d * e : 0.0;
+            F[(n + r) * NW + i] = has_psi ? cf_psi_i * a + cx_psi_i * e : 0.0;
+          }
+      }
     }
 #pragma unroll
     for (int r = 0; r < n; ++r) {
