@@ -84,7 +84,7 @@ struct Dims {
   X(dynf, kCoopMlp ? Q * S::n : 0) X(dynJ, kCoopMlp ? Q * S::n * NW : 0) X(dynH, kCoopMlp ? Q * S::NWP : 0)           \
   X(lam, St * NC) X(z, ldq * NW) X(rb, ldq * NW) X(dz, ldq * NW) X(tv, ldq * NW) X(fixm, (Q + 1) / 2)                   \
   X(W, Q * D::WSZ) X(gl, ldq * NW) X(zL, ldq * NW) X(zU, ldq * NW) X(lbr, ldq * NW) X(ubr, ldq * NW)                    \
-  X(sig, ldq * NW) X(rsl, ldq * NW) X(rsu, ldq * NW) X(dzL, ldq * NW) X(dzU, ldq * NW) X(zt, ldq * NW)                  \
+  X(sig, ldq * NW) X(rsl, ldq * NW) X(rsu, ldq * NW) X(dzL, ldq * NW) X(dzU, ldq * NW)                  \
   X(phi, Q * NC) X(psi, Q * NC) X(c, St * NC) X(sch, St * NC) X(ct, St * NC)                                          \
   X(dz2, ldq * NW) X(csoc, St * NC) X(dl2, St * NC)                                                                   \
   X(ext, scheme_is_lifted<S>::value ? 6 * Q * NW + St * NC : 0)
@@ -264,7 +264,8 @@ struct WsLamView {
 // iterate of the slot (element-major)
 struct WsZView {
   const double* z; int ldq;
-  MYR_HDI double operator()(int q, int i) const { return z[i * ldq + q]; }
+  const double* step; double a;   // optional trial point z + a * step (step == nullptr: the iterate itself)
+  MYR_HDI double operator()(int q, int i) const { return step ? z[i * ldq + q] + a * step[i * ldq + q] : z[i * ldq + q]; }
 };
 
 // ------------------------------------------------------------------ affine role Jacobians (scheme_is_affine)
@@ -291,8 +292,11 @@ MYR_HDI void affine_combine(const Problem& P, int q, const double* dp, const dou
 // Evaluates every node at the point zv (element-major node vector: the iterate or a trial point) and stores the node
 // arrays in the slot.  MODE as in schemes.cuh; MODE 2 also leaves  grad f + J^T lam  (zero on fixed variables) in rb.
 // Returns this thread's part of the objective (the caller reduces it together with its other sums).
+// step / a / blog: line-search trials evaluate z + a * step directly (the trial point is never stored) and return the
+// thread's part of the barrier log-sum of the trial slacks.
 template <class S, int MODE>
-MYR_HDI double eval_nodes(const Problem& P, const WS<S>& ws, const double* zv) {
+MYR_HDI double eval_nodes(const Problem& P, const WS<S>& ws, const double* zv, const double* step = nullptr, double a_step = 0.0,
+                          double* blog = nullptr) {
   using D = Dims<S>;
   constexpr int NW = S::NW, NC = S::NC;
   const int Q = ws.Q;
@@ -300,7 +304,7 @@ MYR_HDI double eval_nodes(const Problem& P, const WS<S>& ws, const double* zv) {
   bool have_pre = false;
 #ifdef __CUDA_ARCH__
   if constexpr (Layout<S>::kCoopMlp) {
-    mlp_nodes_pass<S, MODE>(P, Q, WsZView{zv, ws.ldq}, WsLamView<NC>{ws.lam}, ws.dynf, ws.dynJ, ws.dynH, ws.mlp_scr, ws.theta);
+    mlp_nodes_pass<S, MODE>(P, Q, WsZView{zv, ws.ldq, step, a_step}, WsLamView<NC>{ws.lam}, ws.dynf, ws.dynJ, ws.dynH, ws.mlp_scr, ws.theta);
     have_pre = true;
   }
 #endif
@@ -310,6 +314,20 @@ MYR_HDI double eval_nodes(const Problem& P, const WS<S>& ws, const double* zv) {
     double v[NW], lp[NC], ls[NC];
 #pragma unroll
     for (int i = 0; i < NW; ++i) v[i] = zv[i * ws.ldq + q];
+    if (MODE == 0 && step) {
+      const uint32_t fm = ws.fix()[q];
+      LogProd lpq;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) {
+        const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i);
+        v[i] += a_step * step[i * ws.ldq + q];
+        if (!((fm >> i) & 1u)) {
+          if (lo > -INFINITY) lpq.mul(v[i] - lo);
+          if (hi < INFINITY) lpq.mul(hi - v[i]);
+        }
+      }
+      *blog += lpq.value();
+    }
     const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
     if (MODE == 2) {
 #pragma unroll
@@ -1394,6 +1412,7 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
   bool soc_armed = false;
   double f = 0.0, E0 = INFINITY, cinf = INFINITY, c1 = 0.0;
   const double mu_floor = fmax(O.mu_min, O.tol / 10.0);
+  const double inv_kappa_sigma = 1.0 / O.kappa_sigma;
 
   while (true) {
     // ---------------- K1: evaluate with derivatives; rb = grad f + J^T lam
@@ -1454,8 +1473,8 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = NQ(z, q, i), zl = NQ(zL, q, i), zu = NQ(zU, q, i);
       double sg = 0.0, rbv = NQ(rb, q, i), r1 = 0.0, r2 = 0.0;
       if (!fixed) {
-        if (lo > -INFINITY) { r1 = 1.0 / (x - lo); sg += zl * r1; rbv -= mu * r1; }
-        if (hi < INFINITY) { r2 = 1.0 / (hi - x); sg += zu * r2; rbv += mu * r2; }
+        if (lo > -INFINITY) { r1 = pivot_rcp(x - lo); sg += zl * r1; rbv -= mu * r1; }
+        if (hi < INFINITY) { r2 = pivot_rcp(hi - x); sg += zu * r2; rbv += mu * r2; }
       }
       NQ(rsl, q, i) = r1; NQ(rsu, q, i) = r2;
       NQ(sig, q, i) = sg;
@@ -1502,12 +1521,12 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
         if (r1 != 0.0) {
           dl = mu * r1 - zl - zl * r1 * d;
           m_pr = fmax(m_pr, -d * r1);
-          if (dl < 0.0) m_du = fmax(m_du, -dl / zl);
+          if (dl < 0.0) m_du = fmax(m_du, -dl * pivot_rcp(zl));
         }
         if (r2 != 0.0) {
           du = mu * r2 - zu + zu * r2 * d;
           m_pr = fmax(m_pr, d * r2);
-          if (du < 0.0) m_du = fmax(m_du, -du / zu);
+          if (du < 0.0) m_du = fmax(m_du, -du * pivot_rcp(zu));
         }
       }
       NQ(dzL, q, i) = dl;
@@ -1556,24 +1575,10 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       const double a = soc ? a2 : alpha;
       const double* step = soc ? ws.dz2 : ws.dz;
       ls_used = ls;
-      // ---- trial point z + a * step, its barrier log-sum, objective and constraints
+      // ---- trial point z + a * step (formed per node inside the evaluation, never stored), its barrier log-sum,
+      // objective and constraints
       double blog = 0.0;
-      {
-        LogProd lpq;
-        MYR_FOR_VARS(it) {
-          const int q = it.q, i = it.i;
-          const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i);
-          const double x = NQ(z, q, i) + a * step[i * ws.ldq + q];
-          NQ(zt, q, i) = x;
-          if (!((ws.fix()[q] >> i) & 1u)) {
-            if (lo > -INFINITY) lpq.mul(x - lo);
-            if (hi < INFINITY) lpq.mul(hi - x);
-          }
-        }
-        blog = lpq.value();
-      }
-      MYR_SYNC();   // eval_nodes reads whole nodes of the trial point
-      const double ft_part = eval_nodes<S, 0>(P, ws, ws.zt);
+      const double ft_part = eval_nodes<S, 0>(P, ws, ws.z, step, a, &blog);
       MYR_SYNC();
       double ci_t = 0.0, c1_t = 0.0;
       stage_constraints<S>(P, ws, ws.ct, ci_t, c1_t);
@@ -1607,8 +1612,9 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       }
     }
     const double* dl_acc = ws.dlam;
+    const double* step_acc = ws.dz;
     if (accepted && soc) {  // the multiplier step of the corrected system goes with the corrected primal step
-      dl_acc = ws.dl2;
+      dl_acc = ws.dl2; step_acc = ws.dz2;
       alpha = a2;
     }
     hard_iters = ls_used >= 4 ? hard_iters + 1 : 0;
@@ -1623,16 +1629,16 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     MYR_FOR_VARS(it) {
       const int q = it.q, i = it.i;
       if ((ws.fix()[q] >> i) & 1u) continue;
-      const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = NQ(zt, q, i);
+      const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = NQ(z, q, i) + alpha * step_acc[i * ws.ldq + q];   // the accepted trial point
       const double zl = NQ(zL, q, i), zu = NQ(zU, q, i), dl = NQ(dzL, q, i), du = NQ(dzU, q, i);
       NQ(z, q, i) = x;
       if (lo > -INFINITY) {
-        const double ms = mu / (x - lo);
-        NQ(zL, q, i) = fmax(fmin(zl + a_du * dl, O.kappa_sigma * ms), ms / O.kappa_sigma);
+        const double ms = mu * pivot_rcp(x - lo);
+        NQ(zL, q, i) = fmax(fmin(zl + a_du * dl, O.kappa_sigma * ms), ms * inv_kappa_sigma);
       }
       if (hi < INFINITY) {
-        const double ms = mu / (hi - x);
-        NQ(zU, q, i) = fmax(fmin(zu + a_du * du, O.kappa_sigma * ms), ms / O.kappa_sigma);
+        const double ms = mu * pivot_rcp(hi - x);
+        NQ(zU, q, i) = fmax(fmin(zu + a_du * du, O.kappa_sigma * ms), ms * inv_kappa_sigma);
       }
     }
     for (int k = MYR_TID; k < ncn; k += MYR_NT) ws.lam[k] += alpha * dl_acc[k];
