@@ -392,10 +392,13 @@ MYR_HDI double eval_nodes(const Problem& P, const WS<S>& ws, const double* zv, c
   return fsum;
 }
 
-// stage constraints from node role values; writes cdst (stage-major) and accumulates this thread's (max |c|, sum |c|)
+// stage constraints from node role values; writes cdst (stage-major) and accumulates this thread's (max |c|, sum |c|).
+// mag (optional) accumulates the sum of the MAGNITUDES of the role values that were added up: eps * mag is the rounding
+// noise of sum |c|, which the line search must not mistake for an increase of the infeasibility.
 template <class S>
-MYR_HDI void stage_constraints(const Problem& P, const WS<S>& ws, double* cdst, double& mx, double& sm) {
+MYR_HDI void stage_constraints(const Problem& P, const WS<S>& ws, double* cdst, double& mx, double& sm, double* mag = nullptr) {
   constexpr int NC = S::NC;
+  double mg = 0.0;
   for (int j = MYR_TID; j < ws.St; j += MYR_NT) {
     const int nk = S::stage_nodes(P, j);
     double a[NC];
@@ -405,7 +408,7 @@ MYR_HDI void stage_constraints(const Problem& P, const WS<S>& ws, double* cdst, 
       int role; const int q = S::stage_node(P, j, k, role);
       const double* src = (role ? ws.psi : ws.phi) + q * NC;
 #pragma unroll
-      for (int r = 0; r < NC; ++r) a[r] += src[r];
+      for (int r = 0; r < NC; ++r) { a[r] += src[r]; mg += fabs(src[r]); }
     }
 #pragma unroll
     for (int r = 0; r < NC; ++r) {
@@ -414,6 +417,7 @@ MYR_HDI void stage_constraints(const Problem& P, const WS<S>& ws, double* cdst, 
       mx = fmax(mx, aa); sm += aa;
     }
   }
+  if (mag) *mag += mg;
 }
 
 // ------------------------------------------------------------------ K2 pieces
@@ -1366,6 +1370,14 @@ struct InstPtrs {
 };
 struct InstResult { double f, E0, cinf; int status, iters; };
 
+// host twin: MYR_TRACE=1 prints one line per interior-point iteration (debugging aid for the tests); the device prints
+// the same line only in -DMYR_TRACE_DEVICE builds (tools/build_variant.sh)
+#ifndef __CUDA_ARCH__
+inline bool trace_enabled() { static const bool on = getenv("MYR_TRACE") != nullptr; return on; }
+#elif defined(MYR_TRACE_DEVICE)
+__device__ __forceinline__ bool trace_enabled() { return true; }
+#endif
+
 template <class S>
 MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const InstPtrs& ip, const WS<S>& ws) {
   constexpr int NW = S::NW, NC = S::NC;
@@ -1421,8 +1433,8 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     MYR_SYNC();
     MYR_PH(0);
     // ---------------- constraints, dual residual, complementarity, scaling sums: one fused reduction
-    double cmx = 0.0, csm = 0.0, suml = 0.0;
-    stage_constraints<S>(P, ws, ws.c, cmx, csm);
+    double cmx = 0.0, csm = 0.0, suml = 0.0, cmag = 0.0;
+    stage_constraints<S>(P, ws, ws.c, cmx, csm, &cmag);
     for (int k = MYR_TID; k < ncn; k += MYR_NT) suml += fabs(ws.lam[k]);
     double rdmax = 0.0, szmax = -INFINITY, szmin = INFINITY, sumz = 0.0, nbnd = 0.0, slog = 0.0;
     {
@@ -1444,9 +1456,10 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       slog = lpq.value();
     }
     {
-      double rv[10] = {fpart, cmx, csm, rdmax, szmax, szmin, sumz, nbnd, slog, suml};
-      block_reduce_multi<R_SUM, R_MAX, R_SUM, R_MAX, R_MAX, R_MIN, R_SUM, R_SUM, R_SUM, R_SUM>(rv, ws.red, parity);
+      double rv[11] = {fpart, cmx, csm, rdmax, szmax, szmin, sumz, nbnd, slog, suml, cmag};
+      block_reduce_multi<R_SUM, R_MAX, R_SUM, R_MAX, R_MAX, R_MIN, R_SUM, R_SUM, R_SUM, R_SUM, R_SUM>(rv, ws.red, parity);
       f = rv[0]; cinf = rv[1]; c1 = rv[2]; rdmax = rv[3]; szmax = rv[4]; szmin = rv[5]; sumz = rv[6]; nbnd = rv[7]; slog = rv[8]; suml = rv[9];
+      cmag = rv[10];
     }
     const double sd = fmax(O.s_max, (suml + sumz) / fmax(1.0, (double)ncn + nbnd)) / O.s_max;
     const double sc = nbnd > 0 ? fmax(O.s_max, sumz / nbnd) / O.s_max : 1.0;
@@ -1552,8 +1565,11 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     double alpha = a_pr;
     bool accepted = false;
     double f_t = 0.0;
-    // Armijo with IPOPT's rounding-error relaxation (10 eps |phi|) so that converged iterates are not rejected by cancellation
-    const double armijo_slack = 10.0 * 2.220446049250313e-16 * fabs(phi0);
+    // Armijo with IPOPT's rounding-error relaxation (10 eps |phi|) so that converged iterates are not rejected by
+    // cancellation.  The infeasibility term gets its own allowance: sum |c| is a sum of differences of O(|x|) role values
+    // and cannot be evaluated more accurately than eps * (sum of their magnitudes); with states of order 1e3 (SEIR) that
+    // noise times nu is far above 10 eps |phi| and made converged iterates stall a hair above the tolerance.
+    const double armijo_slack = 2.220446049250313e-16 * (10.0 * fabs(phi0) + 2.0 * nu * cmag);
     // One loop serves the backtracking trials (soc == false: step dz, length alpha) and the second-order-correction
     // trials (soc == true: step dz2 from kkt_soc_solve, length a2), so the trial evaluation exists once in the code.
     int ls = 0, ks = 0, ls_used = 0;
@@ -1617,6 +1633,11 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       dl_acc = ws.dl2; step_acc = ws.dz2;
       alpha = a2;
     }
+#if !defined(__CUDA_ARCH__) || defined(MYR_TRACE_DEVICE)
+    if (MYR_TID == 0 && trace_enabled())
+      printf("[ipm] it %3d f %.12e E0 %.3e cinf %.2e rd %.2e mu %.1e delta %.1e a_pr %.3e a_du %.3e alpha %.3e ls %d soc %d acc %d\n",
+              it, f, E0, cinf, rdmax / sd, mu, delta, a_pr, a_du, alpha, ls_used, (int)soc, (int)accepted);
+#endif
     hard_iters = ls_used >= 4 ? hard_iters + 1 : 0;
 #ifndef MYR_SOC_ARM_AFTER
 #define MYR_SOC_ARM_AFTER 2
