@@ -9,8 +9,8 @@
 // arrays; each array is placed either in the CTA's shared memory or in the slot's global-memory part (L2 resident)
 // by a priority list filled greedily against the shared-memory budget (Layout::place): the block-cyclic-reduction
 // scratch first, then the node-block inverses and the Jacobian blocks, then the iterate vectors.
-//   * matrices are "array of blocks": block q at base + q * stride, stride padded to 2 (mod 4) doubles so that
-//     consecutive nodes' 16-byte accesses fall into distinct banks and every element has a compile-time offset;
+//   * matrices are "array of blocks": block q at base + q * stride, stride odd (in doubles) so that consecutive
+//     nodes' 8-byte accesses fall into distinct banks and every element has a compile-time offset;
 //   * node vectors are element-major (base + i * ldq + q): coalesced in global memory, conflict-free in shared;
 //   * stage vectors are stage-major (base + j * NC + r), the layout the cyclic reduction reads.
 #pragma once
@@ -64,17 +64,44 @@ struct scheme_is_affine<S, typename std::enable_if<S::kAffineJ>::type> { static 
 #endif
 
 // ------------------------------------------------------------------ workspace arrays
-// smallest v >= n with v = 2 (mod 4): block strides (see the header comment)
+// smallest v >= n with v = 2 (mod 4)
 MYR_HDI constexpr int pad2(int n) { return ((n + 1) & ~3) + 2; }
+// smallest odd v >= n: stride of per-node blocks.  The compiler emits 64-bit accesses (generic pointers, no alignment
+// facts), for which 16 consecutive nodes hit 16 distinct bank pairs exactly when the stride in doubles is odd.
+MYR_HDI constexpr int oddpad(int n) { return n | 1; }
+
+// Layout of the NC x NC blocks of the cyclic reduction (crD / crU / crVL / crVU): row stride RS, block stride BS, and
+// the POSITION of block i (cr_pos).  A lane group of G lanes owns a block, lane r its row r; consecutive groups work on
+// consecutive positions.  The strides are chosen so that the 16 lanes of a half-warp (4 groups x 4 rows, 8 x 2, ...) fall
+// into 16 distinct bank pairs: 4 x 4 blocks keep dense rows and an odd block stride (17: row offsets {0,4,8,12} + 4
+// consecutive positions), 2 x 2 blocks pad the rows (3 / 6); 8 x 8 blocks keep the dense layout (their scratch already
+// fills the shared memory of an SM at N = 100).
+template <int NC>
+struct CrLay {
+  static constexpr int RS = NC == 2 ? 3 : NC;
+  static constexpr int BS = NC == 2 ? 6 : (NC <= 4 ? oddpad(NC * NC) : pad2(NC * NC));
+};
+// Blocks are stored in ELIMINATION ORDER: the blocks eliminated at level l (i = (2k+1) 2^l) occupy consecutive positions
+// base_l + k, block 0 (the root) comes last -- so the groups of a warp always touch adjacent blocks, at every level (in
+// natural order the active blocks of level l are 2^(l+1) apart and collide in the same banks).
+MYR_HDI int cr_pos(int i, int St) {
+  if (i == 0) return St - 1;
+#ifdef __CUDA_ARCH__
+  const int l = __ffs(i) - 1;
+#else
+  const int l = __builtin_ctz((unsigned)i);
+#endif
+  return (St - 1) - ((St - 1) >> l) + (i >> (l + 1));
+}
 
 template <class S>
 struct Dims {
   static constexpr int NW = S::NW, NC = S::NC, NWP = S::NWP;
   static constexpr bool kAff = scheme_is_affine<S>::value;
-  static constexpr int GS = kAff ? pad2(S::n * NW) : pad2(NC * NW);   // Jacobian block of a node role (affine schemes: J itself)
-  static constexpr int HS = pad2(NWP);       // node-block inverse (symmetric: packed upper triangle)
-  static constexpr int WSZ = pad2(NWP);      // packed Hessian block
-  static constexpr int BS = pad2(NC * NC);   // Schur-complement block
+  static constexpr int GS = kAff ? oddpad(S::n * NW) : oddpad(NC * NW);   // Jacobian block of a node role (affine schemes: J itself)
+  static constexpr int HS = oddpad(NWP);     // node-block inverse (symmetric: packed upper triangle)
+  static constexpr int WSZ = oddpad(NWP);    // packed Hessian block
+  static constexpr int BS = CrLay<NC>::BS;   // Schur-complement block (rows RS = CrLay<NC>::RS apart)
 };
 
 // X(name, doubles): in shared-memory PRIORITY order
@@ -575,7 +602,7 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
                             int& cp, int& cn, int& cz) {
   if (SH >= 1) { MYR_ASSUME_SHARED(D); MYR_ASSUME_SHARED(U); MYR_ASSUME_SHARED(VL); MYR_ASSUME_SHARED(VU); MYR_ASSUME_SHARED(b); MYR_ASSUME_SHARED(x); }
   constexpr int BB = NC * NC;
-  constexpr int BS = pad2(BB);
+  constexpr int RS = CrLay<NC>::RS, BS = CrLay<NC>::BS;
   constexpr int G = CrGroup<NC>::G;
 #ifdef __CUDA_ARCH__
   const int grp = int(threadIdx.x) / G, ngrp = int(blockDim.x) / G;
@@ -593,16 +620,16 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
 #else
 #define MYR_CPH(idx) do { } while (0)
 #endif
-  // ---- pivot-block inverse of block i.  Device: a[] = row rl of the inverse.  Host: Dinv = full inverse.
+  // ---- pivot-block inverse of the block at position pi.  Device: a[] = row rl of the inverse.  Host: Dinv = full inverse.
 #ifdef __CUDA_ARCH__
-  auto pivot_row = [&](int i, bool active, double (&a)[NC]) {
-    const double* Di = D + i * BS;
+  auto pivot_row = [&](int pi, bool active, double (&a)[NC]) {
+    const double* Di = D + pi * BS;
     bool ok; int p_, n_;
     if constexpr (has_closed_inverse<NC>::value) {
       // every lane inverts the whole (small) block redundantly: no cross-lane traffic, and lane rl keeps row rl
       double M[BB], X[BB];
 #pragma unroll
-      for (int e = 0; e < BB; ++e) M[e] = active ? Di[e] : ((e % (NC + 1)) == 0 ? 1.0 : 0.0);   // idle groups invert the identity
+      for (int e = 0; e < BB; ++e) M[e] = active ? Di[(e / NC) * RS + (e % NC)] : ((e % (NC + 1)) == 0 ? 1.0 : 0.0);   // idle groups invert the identity
       small_sym_inverse<NC>(M, X, ok, p_, n_);
       __syncwarp();   // every lane of the group has read ALL rows of D_i before any lane overwrites its row below
 #pragma unroll
@@ -614,7 +641,7 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < NC; ++c) a[c] = (rvalid && active) ? Di[rl * NC + c] : (c == rl ? 1.0 : 0.0);
+      for (int c = 0; c < NC; ++c) a[c] = (rvalid && active) ? Di[rl * RS + c] : (c == rl ? 1.0 : 0.0);
       coop_inverse<NC, G>(a, rl, ok, p_, n_);
     }
     int z_ = 0;
@@ -624,7 +651,7 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
 #pragma unroll
         for (int r = 0; r < NC; ++r)
 #pragma unroll
-          for (int c = 0; c < NC; ++c) A[r * NC + c] = 0.5 * (Di[r * NC + c] + Di[c * NC + r]);
+          for (int c = 0; c < NC; ++c) A[r * NC + c] = 0.5 * (Di[r * RS + c] + Di[c * RS + r]);
         int p2_, n2_, z2_;
         sym_inverse_inertia<NC>(A, 0u, inv, p2_, n2_, z2_);
         p_ = p2_; n_ = n2_; z_ = z2_;
@@ -641,14 +668,15 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
     if (counter && active) { cp += p_; cn += n_; cz += z_; }
   };
 #else
-  auto pivot_full = [&](int i, double* Dinv) {
-    const double* Di = D + i * BS;
-    for (int e = 0; e < BB; ++e) Dinv[e] = Di[e];
+  auto pivot_full = [&](int pi, double* Dinv) {
+    const double* Di = D + pi * BS;
+    double M[BB];
+    for (int r = 0; r < NC; ++r)
+      for (int c = 0; c < NC; ++c) M[r * NC + c] = Di[r * RS + c];
+    for (int e = 0; e < BB; ++e) Dinv[e] = M[e];
     int p_, n_, z_ = 0;
     bool ok_;
     if constexpr (has_closed_inverse<NC>::value) {
-      double M[BB];
-      for (int e = 0; e < BB; ++e) M[e] = Di[e];
       small_sym_inverse<NC>(M, Dinv, ok_, p_, n_);
     } else {
       ok_ = gj_inverse_full<NC>(Dinv, p_, n_);
@@ -656,7 +684,7 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
     if (!ok_) {
       double A[BB];
       for (int r = 0; r < NC; ++r)
-        for (int c = 0; c < NC; ++c) A[r * NC + c] = 0.5 * (Di[r * NC + c] + Di[c * NC + r]);
+        for (int c = 0; c < NC; ++c) A[r * NC + c] = 0.5 * (M[r * NC + c] + M[c * NC + r]);
       sym_inverse_inertia<NC>(A, 0u, Dinv, p_, n_, z_);
     }
     cp += p_; cn += n_; cz += z_;
@@ -666,35 +694,37 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
   for (; s < St; s <<= 1, ++ls) {
     const int nodd = (St + s - 1) >> (ls + 1);          // blocks i = (2k+1) s < St
     const int neven = (St + 2 * s - 1) >> (ls + 1);     // blocks i = 2k s < St
+    const int pb = (St - 1) - ((St - 1) >> ls);         // position of the first block eliminated at this level (cr_pos)
     // ---- eliminate the odd blocks: Dinv_i (kept in D), VL_i = Dinv_i U_{i-s}^T, VU_i = Dinv_i U_i, x_i = Dinv_i b_i
     for (int k0 = 0; k0 < nodd; k0 += ngrp) {   // trip count uniform across the CTA (the body contains warp shuffles)
       const int k = k0 + grp;
       const bool active = k < nodd;
       const int i = active ? (2 * k + 1) * s : s;
+      const int pi = active ? pb + k : pb;
       const bool hr = i + s < St;
 #ifdef __CUDA_ARCH__
       double dr[NC];
-      pivot_row(i, active, dr);
+      pivot_row(pi, active, dr);
       if (active && rvalid) {
         const int r = rl;
 #else
       double Dinv[BB];
-      pivot_full(i, Dinv);
+      pivot_full(pi, Dinv);
       for (int r = 0; r < NC; ++r) {
         double dr[NC];
         for (int m = 0; m < NC; ++m) dr[m] = Dinv[r * NC + m];
 #endif
-        const double* Ul = U + (i - s) * BS;
-        const double* Ui = U + i * BS;
-        double* Dd = D + i * BS + r * NC;
-        double* VLd = VL + i * BS + r * NC;
-        double* VUd = VU + i * BS + r * NC;
+        const double* Ul = U + cr_pos(i - s, St) * BS;
+        const double* Ui = U + pi * BS;
+        double* Dd = D + pi * BS + r * RS;
+        double* VLd = VL + pi * BS + r * RS;
+        double* VUd = VU + pi * BS + r * RS;
         double xr = 0.0;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           double vl = 0.0;
 #pragma unroll
-          for (int m = 0; m < NC; ++m) vl += dr[m] * Ul[c * NC + m];
+          for (int m = 0; m < NC; ++m) vl += dr[m] * Ul[c * RS + m];
           VLd[c] = vl;
           xr += dr[c] * b[i * NC + c];
         }
@@ -705,7 +735,7 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
 #pragma unroll
           for (int m = 0; m < NC; ++m)
 #pragma unroll
-            for (int c = 0; c < NC; ++c) vu[c] += dr[m] * Ui[m * NC + c];
+            for (int c = 0; c < NC; ++c) vu[c] += dr[m] * Ui[m * RS + c];
 #pragma unroll
           for (int c = 0; c < NC; ++c) VUd[c] = vu[c];
         }
@@ -720,38 +750,39 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
     for (int k = grp; k < neven; k += ngrp) {
       const int i = 2 * k * s, er = i + s, el = i - s;
       const bool hr = er < St, hl = el >= 0, hrr = hr && er + s < St;
+      const int pi = cr_pos(i, St), per = pb + k, pel = pb + k - 1;
       MYR_CR_ROWS(r) {
         double dn[NC], un[NC];
-        double* Dd = D + i * BS + r * NC;
-        double* Ud = U + i * BS + r * NC;
+        double* Dd = D + pi * BS + r * RS;
+        double* Ud = U + pi * BS + r * RS;
         double bn = b[i * NC + r];
 #pragma unroll
         for (int c = 0; c < NC; ++c) { dn[c] = Dd[c]; un[c] = 0.0; }
         if (hr) {
-          const double* VLe = VL + er * BS;
-          const double* VUe = VU + er * BS;
+          const double* VLe = VL + per * BS;
+          const double* VUe = VU + per * BS;
           const double* xe = x + er * NC;
 #pragma unroll
           for (int m = 0; m < NC; ++m) {
             const double u_ = Ud[m];   // row r of U_i
 #pragma unroll
-            for (int c = 0; c < NC; ++c) dn[c] -= u_ * VLe[m * NC + c];
+            for (int c = 0; c < NC; ++c) dn[c] -= u_ * VLe[m * RS + c];
             bn -= u_ * xe[m];
             if (hrr) {
 #pragma unroll
-              for (int c = 0; c < NC; ++c) un[c] -= u_ * VUe[m * NC + c];
+              for (int c = 0; c < NC; ++c) un[c] -= u_ * VUe[m * RS + c];
             }
           }
         }
         if (hl) {
-          const double* Ue = U + el * BS;
-          const double* VUe = VU + el * BS;
+          const double* Ue = U + pel * BS;
+          const double* VUe = VU + pel * BS;
           const double* xe = x + el * NC;
 #pragma unroll
           for (int m = 0; m < NC; ++m) {
-            const double u_ = Ue[m * NC + r];   // column r of U_el = row r of U_el^T
+            const double u_ = Ue[m * RS + r];   // column r of U_el = row r of U_el^T
 #pragma unroll
-            for (int c = 0; c < NC; ++c) dn[c] -= u_ * VUe[m * NC + c];
+            for (int c = 0; c < NC; ++c) dn[c] -= u_ * VUe[m * RS + c];
             bn -= u_ * xe[m];
           }
         }
@@ -763,25 +794,26 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
     MYR_SYNC();
     MYR_CPH(s == 1 ? 11 : (s == 2 ? 13 : 15));
   }
-  // ---- root (block 0): every lane only reads its own row of D_0 before overwriting it
+  // ---- root (block 0, last position): every lane only reads its own row of D_0 before overwriting it
   {
+    const int p0 = St - 1;
 #ifdef __CUDA_ARCH__
     if (int(threadIdx.x) < 32) {   // warp 0 (group 0 lives there); the shuffles need the whole warp
       double dr[NC];
-      pivot_row(0, grp == 0, dr);
+      pivot_row(p0, grp == 0, dr);
       if (grp == 0 && rvalid) {
         const int r = rl;
 #else
     {
       double Dinv[BB];
-      pivot_full(0, Dinv);
+      pivot_full(p0, Dinv);
       for (int r = 0; r < NC; ++r) {
         double dr[NC];
         for (int m = 0; m < NC; ++m) dr[m] = Dinv[r * NC + m];
 #endif
         double xr = 0.0;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { D[r * NC + c] = dr[c]; xr += dr[c] * b[c]; }
+        for (int c = 0; c < NC; ++c) { D[p0 * BS + r * RS + c] = dr[c]; xr += dr[c] * b[c]; }
         x[r] = xr;
       }
     }
@@ -790,16 +822,17 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
   // ---- back substitution: x_i = (Dinv_i b_i) - VL_i x_{i-s} - VU_i x_{i+s}
   for (s >>= 1, --ls; s >= 1; s >>= 1, --ls) {
     const int nodd = (St + s - 1) >> (ls + 1);
+    const int pb = (St - 1) - ((St - 1) >> ls);
     for (int k = grp; k < nodd; k += ngrp) {
-      const int i = (2 * k + 1) * s;
+      const int i = (2 * k + 1) * s, pi = pb + k;
       MYR_CR_ROWS(r) {
         double a = x[i * NC + r];
-        const double* VLd = VL + i * BS + r * NC;
+        const double* VLd = VL + pi * BS + r * RS;
         const double* xl = x + (i - s) * NC;
 #pragma unroll
         for (int m = 0; m < NC; ++m) a -= VLd[m] * xl[m];
         if (i + s < St) {
-          const double* VUd = VU + i * BS + r * NC;
+          const double* VUd = VU + pi * BS + r * RS;
           const double* xr_ = x + (i + s) * NC;
 #pragma unroll
           for (int m = 0; m < NC; ++m) a -= VUd[m] * xr_[m];
@@ -817,31 +850,33 @@ MYR_HDI void block_cr_solve(int St, double* D, double* U, double* VL, double* VU
 // b_i -= VU_e^T b_e (left neighbour e = i-s), which only needs data of already-final eliminated nodes.
 template <int NC>
 MYR_HDN void block_cr_resolve(int St, const double* D, const double* VL, const double* VU, double* b, double* x) {
-  constexpr int BS = pad2(NC * NC);
-  int s = 1;
-  for (; s < St; s <<= 1) {
-    for (int i = 2 * MYR_TID * s; i < St; i += 2 * MYR_NT * s) {
+  constexpr int RS = CrLay<NC>::RS, BS = CrLay<NC>::BS;
+  int s = 1, ls = 0;
+  for (; s < St; s <<= 1, ++ls) {
+    const int pb = (St - 1) - ((St - 1) >> ls);
+    for (int k = MYR_TID; 2 * k * s < St; k += MYR_NT) {
+      const int i = 2 * k * s;
       double bn[NC];
 #pragma unroll
       for (int r = 0; r < NC; ++r) bn[r] = b[i * NC + r];
       const int er = i + s, el = i - s;
       if (er < St) {
-        const double* V = VL + er * BS;
+        const double* V = VL + (pb + k) * BS;
 #pragma unroll
         for (int r = 0; r < NC; ++r) {
           double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < NC; ++k) a += V[k * NC + r] * b[er * NC + k];
+          for (int kk = 0; kk < NC; ++kk) a += V[kk * RS + r] * b[er * NC + kk];
           bn[r] -= a;
         }
       }
       if (el >= 0) {
-        const double* V = VU + el * BS;
+        const double* V = VU + (pb + k - 1) * BS;
 #pragma unroll
         for (int r = 0; r < NC; ++r) {
           double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < NC; ++k) a += V[k * NC + r] * b[el * NC + k];
+          for (int kk = 0; kk < NC; ++kk) a += V[kk * RS + r] * b[el * NC + kk];
           bn[r] -= a;
         }
       }
@@ -851,33 +886,36 @@ MYR_HDN void block_cr_resolve(int St, const double* D, const double* VL, const d
     MYR_SYNC();
   }
   if (MYR_TID == 0) {
+    const double* D0 = D + (St - 1) * BS;
 #pragma unroll
     for (int r = 0; r < NC; ++r) {
       double a = 0.0;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) a += D[r * NC + k] * b[k];
+      for (int k = 0; k < NC; ++k) a += D0[r * RS + k] * b[k];
       x[r] = a;
     }
   }
   MYR_SYNC();
-  for (s >>= 1; s >= 1; s >>= 1) {
-    for (int i = (2 * MYR_TID + 1) * s; i < St; i += 2 * MYR_NT * s) {
+  for (s >>= 1, --ls; s >= 1; s >>= 1, --ls) {
+    const int pb = (St - 1) - ((St - 1) >> ls);
+    for (int k = MYR_TID; (2 * k + 1) * s < St; k += MYR_NT) {
+      const int i = (2 * k + 1) * s;
       double xi[NC];
-      const double* Di = D + i * BS;
-      const double* VLi = VL + i * BS;
-      const double* VUi = VU + i * BS;
+      const double* Di = D + (pb + k) * BS;
+      const double* VLi = VL + (pb + k) * BS;
+      const double* VUi = VU + (pb + k) * BS;
 #pragma unroll
       for (int r = 0; r < NC; ++r) {
         double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) a += Di[r * NC + k] * b[i * NC + k];
+        for (int kk = 0; kk < NC; ++kk) a += Di[r * RS + kk] * b[i * NC + kk];
         xi[r] = a;
       }
 #pragma unroll
       for (int r = 0; r < NC; ++r) {
         double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) a += VLi[r * NC + k] * x[(i - s) * NC + k];
+        for (int kk = 0; kk < NC; ++kk) a += VLi[r * RS + kk] * x[(i - s) * NC + kk];
         xi[r] -= a;
       }
       if (i + s < St) {
@@ -885,7 +923,7 @@ MYR_HDN void block_cr_resolve(int St, const double* D, const double* VL, const d
         for (int r = 0; r < NC; ++r) {
           double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < NC; ++k) a += VUi[r * NC + k] * x[(i + s) * NC + k];
+          for (int kk = 0; kk < NC; ++kk) a += VUi[r * RS + kk] * x[(i + s) * NC + kk];
           xi[r] -= a;
         }
       }
@@ -954,7 +992,7 @@ template <class S, int SH = 0>
 MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, double delta_c, double delta_reg, double& minpr_out,
                         int& parity) {
   using D = Dims<S>;
-  constexpr int NW = S::NW, NC = S::NC, BS = D::BS;
+  constexpr int NW = S::NW, NC = S::NC, BS = D::BS, RS = CrLay<NC>::RS;
   const int Q = ws.Q, St = ws.St;
   double* const crD = ws.crD; double* const crU = ws.crU; double* const crVL = ws.crVL; double* const crVU = ws.crVU;
   double* const crb = ws.crb; double* const Hb = ws.Hinv; const double* const Gb = ws.G; const double* const Fb = ws.F;
@@ -1035,7 +1073,7 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
       };
       if (jp >= 0) {
         const int sl = S::phi_slot(P, q);
-        double* Dst = slotM[sl] + jp * BS;
+        double* Dst = slotM[sl] + cr_pos(jp, St) * BS;
         double* vst = slotV[sl] + jp * NC;
 #pragma unroll
         for (int ga = 0; ga < NG; ++ga)
@@ -1044,15 +1082,16 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
 #pragma unroll
             for (int gb = 0; gb < NG; ++gb)
 #pragma unroll
-              for (int c2 = 0; c2 < n; ++c2) Dst[(ga * n + r) * NC + gb * n + c2] = blk(ap[ga], bp[ga], ap[gb], bp[gb], r, c2);
+              for (int c2 = 0; c2 < n; ++c2) Dst[(ga * n + r) * RS + gb * n + c2] = blk(ap[ga], bp[ga], ap[gb], bp[gb], r, c2);
             vst[ga * n + r] = ap[ga] * Jt[r] + bp[ga] * t[r];
           }
       }
       if (js >= 0) {
         const int sl = S::psi_slot(P, q);
-        double* Dst = slotM[sl] + js * BS;
+        const int pjs = cr_pos(js, St);
+        double* Dst = slotM[sl] + pjs * BS;
         double* vst = slotV[sl] + js * NC;
-        double* Ust = crU + js * BS;
+        double* Ust = crU + pjs * BS;
         const bool link = jp >= 0;   // the node also starts the next stage: coupling block U_js = F Hinv G^T
 #pragma unroll
         for (int ga = 0; ga < NG; ++ga)
@@ -1062,8 +1101,8 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
             for (int gb = 0; gb < NG; ++gb)
 #pragma unroll
               for (int c2 = 0; c2 < n; ++c2) {
-                Dst[(ga * n + r) * NC + gb * n + c2] = blk(as[ga], bs[ga], as[gb], bs[gb], r, c2);
-                if (link) Ust[(ga * n + r) * NC + gb * n + c2] = blk(as[ga], bs[ga], ap[gb], bp[gb], r, c2);
+                Dst[(ga * n + r) * RS + gb * n + c2] = blk(as[ga], bs[ga], as[gb], bs[gb], r, c2);
+                if (link) Ust[(ga * n + r) * RS + gb * n + c2] = blk(as[ga], bs[ga], ap[gb], bp[gb], r, c2);
               }
             vst[ga * n + r] = as[ga] * Jt[r] + bs[ga] * t[r];
           }
@@ -1074,7 +1113,7 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
       const double* Fq = Fb + q * D::GS;
       if (jp >= 0) {
         const int sl = S::phi_slot(P, q);
-        double* Dst = slotM[sl] + jp * BS;
+        double* Dst = slotM[sl] + cr_pos(jp, St) * BS;
         double* vst = slotV[sl] + jp * NC;
   #pragma unroll
         for (int r = 0; r < NC; ++r) {
@@ -1091,7 +1130,7 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
             double a = 0.0;
   #pragma unroll
             for (int i = 0; i < NW; ++i) a += T[i] * Gq[c2 * NW + i];
-            Dst[r * NC + c2] = a;
+            Dst[r * RS + c2] = a;
           }
           double a = 0.0;
   #pragma unroll
@@ -1101,9 +1140,10 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
       }
       if (js >= 0) {
         const int sl = S::psi_slot(P, q);
-        double* Dst = slotM[sl] + js * BS;
+        const int pjs = cr_pos(js, St);
+        double* Dst = slotM[sl] + pjs * BS;
         double* vst = slotV[sl] + js * NC;
-        double* Ust = crU + js * BS;
+        double* Ust = crU + pjs * BS;
         const bool link = jp >= 0;   // the node also starts the next stage: coupling block U_js = F Hinv G^T
   #pragma unroll
         for (int r = 0; r < NC; ++r) {
@@ -1120,7 +1160,7 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
             double a = 0.0;
   #pragma unroll
             for (int i = 0; i < NW; ++i) a += T[i] * Fq[c2 * NW + i];
-            Dst[r * NC + c2] = a;
+            Dst[r * RS + c2] = a;
           }
           if (link) {
   #pragma unroll
@@ -1128,7 +1168,7 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
               double a = 0.0;
   #pragma unroll
               for (int i = 0; i < NW; ++i) a += T[i] * Gq[c2 * NW + i];
-              Ust[r * NC + c2] = a;
+              Ust[r * RS + c2] = a;
             }
           }
           double a = 0.0;
@@ -1145,23 +1185,28 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
   for (int j = MYR_TID; j < St; j += MYR_NT) {
     double Dj[NC * NC], bj[NC];
     const int nk = S::stage_nodes(P, j);
-#pragma unroll
-    for (int i = 0; i < NC * NC; ++i) Dj[i] = slotM[0][j * BS + i];
-#pragma unroll
-    for (int r = 0; r < NC; ++r) bj[r] = NS(c, j, r) - slotV[0][j * NC + r];
-    for (int k = 1; k < nk; ++k) {
-      const double* Ms = slotM[k] + j * BS;
-      const double* vs = slotV[k] + j * NC;
-#pragma unroll
-      for (int i = 0; i < NC * NC; ++i) Dj[i] += Ms[i];
-#pragma unroll
-      for (int r = 0; r < NC; ++r) bj[r] -= vs[r];
-    }
-    double* Dd = crD + j * BS;
+    const int pj = cr_pos(j, St);
 #pragma unroll
     for (int r = 0; r < NC; ++r)
 #pragma unroll
-      for (int c2 = 0; c2 < NC; ++c2) Dd[r * NC + c2] = 0.5 * (Dj[r * NC + c2] + Dj[c2 * NC + r]) + (r == c2 ? delta_c : 0.0);
+      for (int c2 = 0; c2 < NC; ++c2) Dj[r * NC + c2] = slotM[0][pj * BS + r * RS + c2];
+#pragma unroll
+    for (int r = 0; r < NC; ++r) bj[r] = NS(c, j, r) - slotV[0][j * NC + r];
+    for (int k = 1; k < nk; ++k) {
+      const double* Ms = slotM[k] + pj * BS;
+      const double* vs = slotV[k] + j * NC;
+#pragma unroll
+      for (int r = 0; r < NC; ++r)
+#pragma unroll
+        for (int c2 = 0; c2 < NC; ++c2) Dj[r * NC + c2] += Ms[r * RS + c2];
+#pragma unroll
+      for (int r = 0; r < NC; ++r) bj[r] -= vs[r];
+    }
+    double* Dd = crD + pj * BS;
+#pragma unroll
+    for (int r = 0; r < NC; ++r)
+#pragma unroll
+      for (int c2 = 0; c2 < NC; ++c2) Dd[r * RS + c2] = 0.5 * (Dj[r * NC + c2] + Dj[c2 * NC + r]) + (r == c2 ? delta_c : 0.0);
 #pragma unroll
     for (int r = 0; r < NC; ++r) { crb[j * NC + r] = bj[r]; NS(sch, j, r) = bj[r] - NS(c, j, r); }
   }
