@@ -109,8 +109,8 @@ struct Dims {
   X(crD, St * D::BS) X(crU, St * D::BS) X(crVL, St * D::BS) X(crVU, St * D::BS) X(crb, St * NC) X(dlam, St * NC)       \
   X(Hinv, Q * D::HS) X(G, Q * D::GS) X(F, D::kAff ? 0 : Q * D::GS)                                                                  \
   X(dynf, kCoopMlp ? Q * S::n : 0) X(dynJ, kCoopMlp ? Q * S::n * NW : 0) X(dynH, kCoopMlp ? Q * S::NWP : 0)           \
-  X(lam, St * NC) X(z, ldq * NW) X(rb, ldq * NW) X(dz, ldq * NW) X(tv, ldq * NW) X(fixm, (Q + 1) / 2)                   \
-  X(W, Q * D::WSZ) X(gl, ldq * NW) X(zL, ldq * NW) X(zU, ldq * NW) X(lbr, ldq * NW) X(ubr, ldq * NW)                    \
+  X(lam, St * NC) X(z, ldq * NW) X(rb, ldq * NW) X(dz, ldq * NW) X(fixm, (Q + 1) / 2)                                  \
+  X(zL, ldq * NW) X(zU, ldq * NW) X(lbr, ldq * NW) X(ubr, ldq * NW) X(gl, ldq * NW) X(W, Q * D::WSZ)                    \
   X(sig, ldq * NW) X(rsl, ldq * NW) X(rsu, ldq * NW) X(dzL, ldq * NW) X(dzU, ldq * NW)                  \
   X(phi, Q * NC) X(psi, Q * NC) X(c, St * NC) X(sch, St * NC) X(ct, St * NC)                                          \
   X(dz2, ldq * NW) X(csoc, St * NC) X(dl2, St * NC)                                                                   \
@@ -133,11 +133,18 @@ struct Layout {
   int size[A_COUNT];
   MYR_HDI explicit Layout(const Problem& P) {
     Q = S::num_nodes(P); St = S::num_stages(P);
-    ldq = (Q + 3) & ~3;
+    ldq = Q;   // node vectors are element-major with 8-byte accesses: any leading dimension is conflict-free
 #define X(name, sz) size[A_##name] = ((sz) + 1) & ~1;
     MYR_WS_ARRAYS(X)
 #undef X
+    // The coupling blocks crU are dead from the last update phase of the cyclic reduction until the next node phase
+    // writes them again -- exactly the window in which the role values phi / psi (node evaluation -> stage constraints,
+    // main evaluation and line-search trials) and the trial constraints ct are alive: they live inside crU when it is
+    // large enough (block sizes >= 4), i.e. in shared memory whenever the reduction scratch is.
+    alias_u = size[A_crU] >= 2 * Q * NC + St * NC;
+    if (alias_u) size[A_phi] = size[A_psi] = size[A_ct] = 0;
   }
+  bool alias_u;
   // greedy placement against a shared-memory budget (doubles): bit a of the result <=> array a is in shared memory
   MYR_HDI unsigned long long place(long long budget, int& smem_doubles, int& glob_doubles) const {
     unsigned long long mask = 0;
@@ -173,6 +180,7 @@ struct WS {
 #define X(name, sz) if ((mask >> L::A_##name) & 1ull) { name = sp; sp += lay.size[L::A_##name]; } else { name = gp; gp += lay.size[L::A_##name]; }
     MYR_WS_ARRAYS(X)
 #undef X
+    if (lay.alias_u) { phi = crU; psi = crU + Q * L::NC; ct = psi + Q * L::NC; }
     red = nullptr; mlp_scr = nullptr; theta = nullptr; sh = 0;
   }
   MYR_HDI uint32_t* fix() const { return reinterpret_cast<uint32_t*>(fixm); }
@@ -192,6 +200,7 @@ struct VarIter {
   }
 };
 #define MYR_FOR_VARS(it) for (VarIter<S> it(ws); it.valid(); it.next(ws))
+
 
 // Address-space hints.  The slot's arrays are reached through generic pointers (an array may live in shared OR global
 // memory, Layout::place decides at run time); a generic load from shared memory goes through the global-load path --
@@ -990,7 +999,7 @@ MYR_HDI void jt_times(const Problem& P, const WS<S>& ws, int q, const double* dv
 // Returns the inertia-ok flag; minpr = smallest relative pivot of the node blocks (refinement is only worth it when small).
 template <class S, int SH = 0>
 MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, double delta_c, double delta_reg, double& minpr_out,
-                        int& parity) {
+                        int& parity, double mu_apply = -1.0) {
   using D = Dims<S>;
   constexpr int NW = S::NW, NC = S::NC, BS = D::BS, RS = CrLay<NC>::RS;
   const int Q = ws.Q, St = ws.St;
@@ -1006,7 +1015,7 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
 #endif
   // role-product slots: the k-th node block of a stage (phi_slot / psi_slot) writes into its own scratch
   double* const slotM[3] = {crD, crVL, crVU};
-  double* const slotV[3] = {crb, ws.ct, ws.dl2};
+  double* const slotV[3] = {crb, ws.dlam, ws.dl2};   // dlam: dead until the reduction writes the solution (not ct: it may live inside crU)
   int hn = 0, hz = 0;
   double minpr = INFINITY;
   for (int q = MYR_TID; q < Q; q += MYR_NT) {
@@ -1016,8 +1025,26 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
     for (int i = 0; i < NW; ++i)
 #pragma unroll
       for (int j = 0; j < NW; ++j) A[i * NW + j] = Wq[pidx(i, j, NW)];
+    double rbn[NW];
+    if (mu_apply >= 0.0) {
+      // interior-point caller, first factorisation of the iteration: Sigma and the barrier part of the right-hand side
+      // from the reciprocal slacks (kept for inertia-correction retries and the refinement, which read sig / rb)
+      const uint32_t fm = ws.fix()[q];
 #pragma unroll
-    for (int i = 0; i < NW; ++i) A[i * NW + i] += NQ(sig, q, i) + delta_w + delta_reg;
+      for (int i = 0; i < NW; ++i) {
+        const double r1 = NQ(rsl, q, i), r2 = NQ(rsu, q, i), zl = NQ(zL, q, i), zu = NQ(zU, q, i);
+        double sg = 0.0, rbv = NQ(rb, q, i);
+        sg += zl * r1; rbv -= mu_apply * r1;
+        sg += zu * r2; rbv += mu_apply * r2;
+        rbv = ((fm >> i) & 1u) ? 0.0 : rbv;
+        NQ(sig, q, i) = sg; NQ(rb, q, i) = rbv;
+        rbn[i] = rbv;
+        A[i * NW + i] += sg + delta_w + delta_reg;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NW; ++i) { rbn[i] = NQ(rb, q, i); A[i * NW + i] += NQ(sig, q, i) + delta_w + delta_reg; }
+    }
     int p_, n_, z_;
     double pr_;
     sym_inverse<NW>(A, ws.fix()[q], inv, p_, n_, z_, &pr_);
@@ -1032,9 +1059,8 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
     for (int i = 0; i < NW; ++i) {
       double a = 0.0;
 #pragma unroll
-      for (int k = 0; k < NW; ++k) a += inv[i * NW + k] * NQ(rb, q, k);
+      for (int k = 0; k < NW; ++k) a += inv[i * NW + k] * rbn[k];
       t[i] = a;
-      NQ(tv, q, i) = a;
     }
     const int jp = S::phi_stage(P, q), js = S::psi_stage(P, q);
     if constexpr (D::kAff) {
@@ -1223,7 +1249,7 @@ MYR_HDI bool kkt_factor(const Problem& P, const WS<S>& ws, double delta_w, doubl
   return (Hzero == 0) && (Szero == 0) && (Sneg == Hneg);
 }
 
-// dz = -(tv + Hinv J^T dl) for the multiplier step dl (stage-major), tv = Hinv rb; written to the node vector dst.
+// dz = -Hinv (rb + J^T dl) for the multiplier step dl (stage-major); written to the node vector dst.
 // Returns this thread's part of  dz^T H dz = -dz . (rb + J^T dl)  (H dz = -(rb + J^T dl) on the free variables).
 template <class S, int SH = 0>
 MYR_HDI double kkt_backsub(const Problem& P, const WS<S>& ws, const double* dl, double* dst) {
@@ -1238,12 +1264,14 @@ MYR_HDI double kkt_backsub(const Problem& P, const WS<S>& ws, const double* dl, 
     jt_times<S, SH>(P, ws, q, dl, u);
     const double* Hq = Hb + q * D::HS;
 #pragma unroll
+    for (int i = 0; i < NW; ++i) u[i] += NQ(rb, q, i);
+#pragma unroll
     for (int i = 0; i < NW; ++i) {
-      double a = NQ(tv, q, i);
+      double a = 0.0;
 #pragma unroll
       for (int k = 0; k < NW; ++k) a += Hq[pidx(i, k, NW)] * u[k];
       dst[i * ws.ldq + q] = -a;
-      dHd += a * (NQ(rb, q, i) + u[i]);   // a = -dz_i (zero on fixed variables: their rows of Hinv vanish)
+      dHd += a * u[i];   // a = -dz_i (zero on fixed variables: their rows of Hinv vanish)
     }
   }
   return dHd;
@@ -1366,9 +1394,9 @@ MYR_HDI void kkt_refine(const Problem& P, const WS<S>& ws, double delta_w, doubl
 // complete KKT solve (factor, multipliers, primal step, optional refinement): what myr_kkt_solve exposes
 template <class S, int SH = 0>
 MYR_HDI bool kkt_solve(const Problem& P, const WS<S>& ws, double delta_w, double delta_c, double delta_reg, int max_refine, int& parity,
-                       double* dHd_part = nullptr) {
+                       double* dHd_part = nullptr, double mu_apply = -1.0) {
   double minpr;
-  const bool ok = kkt_factor<S, SH>(P, ws, delta_w, delta_c, delta_reg, minpr, parity);
+  const bool ok = kkt_factor<S, SH>(P, ws, delta_w, delta_c, delta_reg, minpr, parity, mu_apply);
   if (!ok) return false;
   const double dHd = kkt_backsub<S, SH>(P, ws, ws.dlam, ws.dz);
   if (dHd_part) *dHd_part = dHd;
@@ -1489,12 +1517,15 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
         const bool fixed = (ws.fix()[q] >> i) & 1u;
         // all loads first, unconditionally: vectors that live in global memory cost one round trip, not one per branch
         const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = NQ(z, q, i), zl = NQ(zL, q, i), zu = NQ(zU, q, i), r0 = NQ(rb, q, i);
-        double rd = 0.0;
+        double rd = 0.0, r1 = 0.0, r2 = 0.0;
         if (!fixed) {
           rd = r0 - zl + zu;
-          if (lo > -INFINITY) { const double sl = x - lo; const double pz = sl * zl; szmax = fmax(szmax, pz); szmin = fmin(szmin, pz); sumz += zl; nbnd += 1.0; lpq.mul(sl); }
-          if (hi < INFINITY) { const double su = hi - x; const double pz = su * zu; szmax = fmax(szmax, pz); szmin = fmin(szmin, pz); sumz += zu; nbnd += 1.0; lpq.mul(su); }
+          if (lo > -INFINITY) { const double sl = x - lo; const double pz = sl * zl; szmax = fmax(szmax, pz); szmin = fmin(szmin, pz); sumz += zl; nbnd += 1.0; lpq.mul(sl); r1 = pivot_rcp(sl); }
+          if (hi < INFINITY) { const double su = hi - x; const double pz = su * zu; szmax = fmax(szmax, pz); szmin = fmin(szmin, pz); sumz += zu; nbnd += 1.0; lpq.mul(su); r2 = pivot_rcp(su); }
         }
+        // reciprocal slacks for the barrier terms (node phase of the KKT solve) and the step-size phase: they do not depend
+        // on mu, so this pass -- which has every operand in registers anyway -- produces them
+        NQ(rsl, q, i) = r1; NQ(rsu, q, i) = r2;
         const double a = (rd != rd) ? INFINITY : fabs(rd);
         rdmax = fmax(rdmax, a);
       }
@@ -1524,22 +1555,8 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     const double tau = fmax(O.tau_min, 1.0 - mu);
 
     MYR_PH(1);
-    // ---------------- barrier gradient rb and Sigma (reciprocal slacks are kept for the step-size phase)
-    MYR_FOR_VARS(it) {
-      const int q = it.q, i = it.i;
-      const bool fixed = (ws.fix()[q] >> i) & 1u;
-      const double lo = NQ(lbr, q, i), hi = NQ(ubr, q, i), x = NQ(z, q, i), zl = NQ(zL, q, i), zu = NQ(zU, q, i);
-      double sg = 0.0, rbv = NQ(rb, q, i), r1 = 0.0, r2 = 0.0;
-      if (!fixed) {
-        if (lo > -INFINITY) { r1 = pivot_rcp(x - lo); sg += zl * r1; rbv -= mu * r1; }
-        if (hi < INFINITY) { r2 = pivot_rcp(hi - x); sg += zu * r2; rbv += mu * r2; }
-      }
-      NQ(rsl, q, i) = r1; NQ(rsu, q, i) = r2;
-      NQ(sig, q, i) = sg;
-      NQ(rb, q, i) = fixed ? 0.0 : rbv;
-    }
-    MYR_SYNC();   // the node phase of kkt_factor reads sig / rb of whole nodes
-
+    // (the barrier gradient  rb -= mu / s_L - mu / s_U  and  Sigma = z_L / s_L + z_U / s_U  are formed per node inside the
+    // KKT node phase, first factorisation attempt only: kkt_factor, mu_apply)
     MYR_PH(2);
     // ---------------- K2: KKT solve with inertia correction (IPOPT Algorithm IC)
     double delta = 0.0, dHd = 0.0;   // dHd: this thread's part of dz^T H dz, from the back-substitution
@@ -1548,13 +1565,13 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       // accurate steps only matter near the solution: refine the linear solve in the end game only
       const int refine = E0 < 1e-3 ? O.max_refine : 0;
 #if defined(__CUDA_ARCH__) && defined(MYR_FORCE_SH)
-      ok = kkt_solve<S, MYR_FORCE_SH>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd);   // experiment: one variant only
+      ok = kkt_solve<S, MYR_FORCE_SH>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd, tries == 0 ? mu : -1.0);   // experiment: one variant only
 #elif defined(__CUDA_ARCH__) && defined(MYR_DISPATCH_SH)
-      if (ws.sh == 2) ok = kkt_solve<S, 2>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd);
-      else if (ws.sh == 1) ok = kkt_solve<S, 1>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd);
-      else ok = kkt_solve<S, 0>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd);
+      if (ws.sh == 2) ok = kkt_solve<S, 2>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd, tries == 0 ? mu : -1.0);
+      else if (ws.sh == 1) ok = kkt_solve<S, 1>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd, tries == 0 ? mu : -1.0);
+      else ok = kkt_solve<S, 0>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd, tries == 0 ? mu : -1.0);
 #else
-      ok = kkt_solve<S, 0>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd);
+      ok = kkt_solve<S, 0>(P, ws, delta, O.delta_c, O.delta_reg, refine, parity, &dHd, tries == 0 ? mu : -1.0);
 #endif
       if (ok) break;
       if (delta == 0.0) delta = (delta_last == 0.0) ? O.delta_0 : fmax(O.delta_min, O.kappa_w_minus * delta_last);

@@ -1,6 +1,4 @@
 #!/bin/bash
+# tools/gpu_ab.sh <tag> [quads]: A/B bench of build/lib_<tag>.so (CARTPOLE-only variant)
 mkdir -p gpurun_out
-: > gpurun_out/ab.log
-python tools/ab_bench.py trap,hs >> gpurun_out/ab.log 2>&1
-for v in "$@"; do MYR_LIB=$PWD/build/lib_$v.so python tools/ab_bench.py trap >> gpurun_out/ab.log 2>&1; done
-cat gpurun_out/ab.log
+MYR_LIB=$PWD/build/lib_$1.so timeout 300 python tools/ab_bench.py ${2:-trap} 2>&1 | grep -v Warn | tee gpurun_out/ab_$1.log
