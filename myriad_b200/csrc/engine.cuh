@@ -25,7 +25,7 @@ struct IpmOpts {
   int max_iter;
   int max_ls;
   int acceptable_iter;
-  int reserved;
+  int use_filter;     // line search: a trial point is accepted by the l1-merit Armijo test OR by IPOPT's filter rules
   double tol, acceptable_tol;
   double mu_init, mu_min, kappa_eps, kappa_mu, theta_mu, tau_min;
   double bound_push, bound_frac, bound_relax, kappa_sigma, s_max;
@@ -169,6 +169,7 @@ struct WS {
   MYR_WS_ARRAYS(X)
 #undef X
   double* red;       // reduction scratch: 2 * kRedStride doubles
+  double* filt;      // line-search filter: 2 * kFilterMax doubles (shared memory; null on the host, which keeps it on the stack)
   double* mlp_scr;   // NODE systems: scratch of the cooperative MLP pass (shared memory), else null
   const double* theta;   // NODE systems: shared-memory copy of the MLP weights (null: read the caller's vector)
   int vq0, vi0, vqs, vis;   // VarIter: start (node, component) of this thread and its stride
@@ -181,7 +182,7 @@ struct WS {
     MYR_WS_ARRAYS(X)
 #undef X
     if (lay.alias_u) { phi = crU; psi = crU + Q * L::NC; ct = psi + Q * L::NC; }
-    red = nullptr; mlp_scr = nullptr; theta = nullptr; sh = 0;
+    red = nullptr; filt = nullptr; mlp_scr = nullptr; theta = nullptr; sh = 0;
   }
   MYR_HDI uint32_t* fix() const { return reinterpret_cast<uint32_t*>(fixm); }
 };
@@ -222,6 +223,8 @@ struct VarIter {
 // red: 2 * kRedStride doubles of shared memory, used alternately (parity) so that no leading barrier is needed.
 constexpr int kRedMaxK = 12;
 constexpr int kRedStride = 8 * kRedMaxK;
+constexpr int kFilterMax = 16;                                   // entries (theta, phi) of the line-search filter
+constexpr int kFixedScratch = 2 * kRedStride + 2 * kFilterMax;   // per-CTA shared memory ahead of the slot arrays
 enum RedOp : int { R_SUM = 0, R_MAX = 1, R_MIN = 2 };
 MYR_HDI double red_apply(int op, double a, double b) { return op == R_SUM ? a + b : (op == R_MAX ? fmax(a, b) : fmin(a, b)); }
 
@@ -1498,6 +1501,18 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
   double f = 0.0, E0 = INFINITY, cinf = INFINITY, c1 = 0.0;
   const double mu_floor = fmax(O.mu_min, O.tol / 10.0);
   const double inv_kappa_sigma = 1.0 / O.kappa_sigma;
+  // Line-search filter (Waechter & Biegler 2006, section 2.3; IPOPT's defaults): pairs (theta, phi) = (sum |c|, barrier
+  // objective) that a trial point must improve on.  A ring of kFilterMax entries, emptied whenever mu changes (phi
+  // depends on mu).  All threads carry the same count; thread 0 writes the entries (accept phase, before its barrier).
+  constexpr double kGammaTheta = 1e-5, kGammaPhi = 1e-8, kEtaPhi = 1e-8, kSTheta = 1.1, kSPhi = 2.3;
+#ifdef __CUDA_ARCH__
+  double* const filt = ws.filt;
+#else
+  double filt_host[2 * kFilterMax];
+  double* const filt = filt_host;
+#endif
+  int nfilt = 0;
+  double theta_max = -1.0, theta_min = -1.0, mu_filter = mu;
 
   while (true) {
     // ---------------- K1: evaluate with derivatives; rb = grad f + J^T lam
@@ -1553,6 +1568,8 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     if (it >= O.max_iter) { status = ST_MAXITER; break; }
     while (mu > mu_floor && Emu(mu) <= O.kappa_eps * mu) mu = fmax(mu_floor, fmin(O.kappa_mu * mu, pow(mu, O.theta_mu)));
     const double tau = fmax(O.tau_min, 1.0 - mu);
+    if (theta_max < 0.0) { theta_max = 1e4 * fmax(1.0, c1); theta_min = 1e-4 * fmax(1.0, c1); }
+    if (mu != mu_filter) { nfilt = 0; mu_filter = mu; }
 
     MYR_PH(1);
     // (the barrier gradient  rb -= mu / s_L - mu / s_U  and  Sigma = z_L / s_L + z_U / s_U  are formed per node inside the
@@ -1624,6 +1641,10 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     }
     const double Dm = dphi - nu * c1;
     const double phi0 = f - mu * slog + nu * c1;
+    const double bphi0 = f - mu * slog;   // barrier objective of the iterate (filter)
+    const double sw_lhs = (O.use_filter && dphi < 0.0 && c1 <= theta_min) ? pow(-dphi, kSPhi) : 0.0;
+    const double sw_rhs = (O.use_filter && dphi < 0.0 && c1 <= theta_min) ? pow(c1, kSTheta) : INFINITY;
+    bool ftype = false;
     double alpha = a_pr;
     bool accepted = false;
     double f_t = 0.0;
@@ -1667,6 +1688,23 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       }
       const double phit = f_t - mu * blog + nu * c1_t;
       if (isfinite(phit) && phit <= phi0 + O.eta * alpha * Dm + armijo_slack) { accepted = true; break; }
+      // Not enough decrease of the l1 merit function.  IPOPT's filter rules accept the point all the same when it makes
+      // sufficient progress in EITHER the infeasibility or the barrier objective (and is not dominated by an earlier
+      // iterate): far from the solution the merit test rejects long steps that cut the infeasibility because the barrier
+      // objective rises, and the iteration crawls with steps of a few percent (CARTPOLE: 27 of one instance's 41
+      // iterations).  The merit test above stays as the alternative that needs no restoration phase.
+      if (O.use_filter && isfinite(phit) && c1_t <= theta_max) {
+        const double bphi_t = f_t - mu * blog;
+        bool fok = true;
+        const int nf = nfilt < kFilterMax ? nfilt : kFilterMax;
+        for (int j = 0; j < nf; ++j)
+          if (c1_t >= (1.0 - kGammaTheta) * filt[2 * j] && bphi_t >= filt[2 * j + 1] - kGammaPhi * filt[2 * j]) fok = false;
+        if (fok) {
+          if (c1 <= theta_min && sw_lhs * alpha > sw_rhs) {   // switching condition: an objective-type step needs Armijo on phi
+            if (bphi_t <= bphi0 + kEtaPhi * alpha * dphi + armijo_slack) { accepted = true; ftype = true; break; }
+          } else if (c1_t <= (1.0 - kGammaTheta) * c1 || bphi_t <= bphi0 - kGammaPhi * c1) { accepted = true; break; }
+        }
+      }
       if (!soc) {
         // second-order correction (IPOPT A-5.5 .. A-5.9): the full step was rejected without reducing the infeasibility,
         // typically because the constraint curvature along dz outweighs the predicted decrease (Maratos effect).
@@ -1725,6 +1763,13 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       }
     }
     for (int k = MYR_TID; k < ncn; k += MYR_NT) ws.lam[k] += alpha * dl_acc[k];
+    if (O.use_filter && !ftype) {   // the iterate just left joins the filter (unless the step was an objective-type step)
+      if (MYR_TID == 0) {
+        const int pos = nfilt % kFilterMax;
+        filt[2 * pos] = (1.0 - kGammaTheta) * c1; filt[2 * pos + 1] = bphi0 - kGammaPhi * c1;
+      }
+      ++nfilt;
+    }
     MYR_SYNC();
     ++it;
   }

@@ -509,7 +509,7 @@ struct SlotPlan {
       theta_doubles = (M.boff[M.L - 1] + M.size[M.L] + 1) & ~1;
       mlp = (size_t)(mlp_scratch_doubles<S>(P.mlp) + theta_doubles) * sizeof(double);
     }
-    fixed_bytes = 2 * kRedStride * sizeof(double) + mlp;
+    fixed_bytes = kFixedScratch * sizeof(double) + mlp;
     auto budget = [&](int k) -> long long {
       long long per = 233472 / k - 1024;
       if (per > 232448) per = 232448;
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(256) kkt_kernel(Problem P, const double* Hblk,
                                                   unsigned long long mask, double* work, long long slot_stride) {
   extern __shared__ __align__(16) double smem[];
   const Layout<S> L(P);
-  WS<S> ws(L, mask, smem + 2 * kRedStride, work + (long long)blockIdx.x * slot_stride);
+  WS<S> ws(L, mask, smem + kFixedScratch, work + (long long)blockIdx.x * slot_stride);
   ws.red = smem;
   for (int b = blockIdx.x; b < P.B; b += gridDim.x)
     kkt_instance<S>(P, b, Hblk, Jblk, sigma, rhs_z, rhs_c, dw, dc, dz, dlam, inertia_ok, ws);
@@ -634,7 +634,7 @@ int sys_kkt_solve(const MyrDesc* desc, int B, const double* Hblk, const double* 
     if (B == 0) return (int)MYR_OK;
     const Layout<S> L(P);
     SlotPlan<S> sp(P, 1);
-    sp.smem_bytes -= sp.fixed_bytes - 2 * kRedStride * sizeof(double);   // no MLP scratch in this kernel
+    sp.smem_bytes -= sp.fixed_bytes - kFixedScratch * sizeof(double);   // no MLP scratch in this kernel
     const int threads = threads_for(L.Q);
     int err;
     const int grid = persistent_grid(kkt_kernel<S>, threads, sp.smem_bytes, B, &err);
@@ -704,6 +704,8 @@ inline IpmOpts make_opts(const MyrIpmOpts* o) {
   r.delta_min = 1e-20; r.delta_0 = 1e-4; r.delta_max = 1e40; r.delta_c = 0.0;
   r.kappa_w_minus = 1.0 / 3.0; r.kappa_w_plus = 8.0; r.kappa_w_plus_first = 100.0;
   r.eta = 1e-4; r.rho = 0.1;
+  r.use_filter = 1;
+  if (const char* e = getenv("MYR_FILTER")) r.use_filter = atoi(e) != 0;   // A/B knob: 0 = l1-merit acceptance only
   r.delta_reg = 1e-8; r.max_refine = 1;
   r.max_soc = (o && o->max_soc != 0) ? (o->max_soc > 0 ? o->max_soc : 0) : 4;
   if (const char* e = getenv("MYR_MU_INIT")) r.mu_init = atof(e);          // tuning knobs (debug)
@@ -726,9 +728,10 @@ ipm_kernel(Problem P, IpmOpts O, IpmIO io, unsigned long long mask, int smem_dou
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_next;
   const Layout<S> L(P);
-  WS<S> ws(L, mask, smem + 2 * kRedStride, work + (long long)blockIdx.x * slot_stride);
+  WS<S> ws(L, mask, smem + kFixedScratch, work + (long long)blockIdx.x * slot_stride);
   ws.red = smem;
-  ws.mlp_scr = smem + 2 * kRedStride + smem_doubles + theta_doubles;
+  ws.filt = smem + 2 * kRedStride;
+  ws.mlp_scr = smem + kFixedScratch + smem_doubles + theta_doubles;
   {
     using LY = Layout<S>;
     const unsigned long long cr = (1ull << LY::kCrArrays) - 1ull;
@@ -736,7 +739,7 @@ ipm_kernel(Problem P, IpmOpts O, IpmIO io, unsigned long long mask, int smem_dou
     ws.sh = (mask & cr) == cr ? (((mask & nodem) == nodem) ? 2 : 1) : 0;
   }
   if (Layout<S>::kCoopMlp) {   // weights into shared memory once per (persistent) CTA
-    double* th = smem + 2 * kRedStride + smem_doubles;
+    double* th = smem + kFixedScratch + smem_doubles;
     for (int e = threadIdx.x; e < theta_doubles; e += blockDim.x) th[e] = e < P.mlp.boff[P.mlp.L - 1] + P.mlp.size[P.mlp.L] ? P.mlp.theta[e] : 0.0;
     ws.theta = th;
     __syncthreads();
