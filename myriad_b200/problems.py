@@ -92,7 +92,37 @@ def _rollout_guess(tr: Transcription, x0s: torch.Tensor, steps: int) -> torch.Te
 
 
 def build_batch(tr: Transcription, x0s: torch.Tensor):
-  """-> (z0, lb, ub), each [B, nvars] float64 on x0s.device"""
+  """-> (z0, lb, ub), each [B, nvars] float64 on x0s.device.
+
+  Systems whose target state is fully specified (the guess is a straight line from x0 to x_T, no rollout) take a
+  vectorised path: the bounds of an instance differ from those of any other only in the start-state rows, so one template
+  per (transcription, device) is built by the general code below and the start states are written into copies of it --
+  a dozen launches instead of one per state component and bound row (it is inside the end-to-end timed region)."""
+  xT = None if tr.system.x_T is None else list(tr.system.x_T)
+  if xT is None or any(v is None for v in xT) or x0s.shape[0] == 0:
+    return _build_batch_general(tr, x0s)
+  cache = tr.__dict__.setdefault("_bb_cache", {})
+  key = str(x0s.device)
+  if key not in cache:
+    _, lb1, ub1 = _build_batch_general(tr, x0s[:1])
+    f64 = dict(dtype=torch.float64, device=x0s.device)
+    cache[key] = (lb1[0].clone(), ub1[0].clone(), torch.arange(tr.nx_nodes, **f64),
+                  torch.as_tensor(np.asarray(xT, dtype=np.float64), **f64))
+  lb_t, ub_t, k, xt = cache[key]
+  B, n, L = x0s.shape[0], tr.n, tr.nx_nodes
+  step = (xt[None, :] - x0s) / (L - 1)                           # jnp.linspace(x0_i, xT_i, L): a + k * ((b - a) / (L - 1)),
+  xg = x0s[:, None, :] + k[None, :, None] * step[:, None, :]     # last entry exactly b (same arithmetic as _linspace_rows)
+  xg[:, -1, :] = xt
+  z0 = torch.zeros(B, lb_t.shape[0], dtype=torch.float64, device=x0s.device)
+  z0[:, :L * n] = xg.reshape(B, -1)
+  lb = lb_t.unsqueeze(0).repeat(B, 1)
+  ub = ub_t.unsqueeze(0).repeat(B, 1)
+  lb[:, :n] = x0s
+  ub[:, :n] = x0s
+  return z0, lb, ub
+
+
+def _build_batch_general(tr: Transcription, x0s: torch.Tensor):
   s = tr.system
   B = x0s.shape[0]
   dev = x0s.device

@@ -201,6 +201,36 @@ def test_random_start_states_reach_the_oracle_basin(be):
   assert abs(out["obj"][0] - float(fx["sol_cost"])) <= 5e-5 * abs(float(fx["sol_cost"]))
 
 
+def test_filter_line_search_keeps_the_optima_and_cuts_iterations(monkeypatch):
+  """The line search accepts a trial point by the l1-merit Armijo test OR by IPOPT's filter rules (engine.cuh).  On 64
+  rows of the bench workload (host twin; the device runs the same templates) the filter must (a) converge every row,
+  (b) end in the same optimum as the merit-only line search, (c) need clearly fewer iterations."""
+  from myriad_b200 import problems as PR
+  import torch
+  tr = product_transcription("c2_cartpole_trap_100")
+  fx = load("c2_cartpole_trap_100")
+  B = 64
+  x0 = PR.sample_x0(tr.system, B).numpy()
+  z0 = np.tile(fx["guess"], (B, 1)); lb = np.tile(fx["bounds"][:, 0], (B, 1)); ub = np.tile(fx["bounds"][:, 1], (B, 1))
+  n, L = tr.n, tr.nx_nodes
+  xT = np.asarray(tr.system.x_T, dtype=np.float64)
+  k = np.arange(L, dtype=np.float64)
+  for b in range(B):
+    xg = x0[b][None, :] + k[:, None] * ((xT - x0[b]) / (L - 1))[None, :]
+    xg[-1] = xT
+    z0[b, :L * n] = xg.reshape(-1)
+    lb[b, :n] = x0[b]; ub[b, :n] = x0[b]
+  host = _Host()
+  monkeypatch.setenv("MYR_FILTER", "0")
+  merit = host.solve(tr, z0, lb, ub)
+  monkeypatch.setenv("MYR_FILTER", "1")
+  filt = host.solve(tr, z0, lb, ub)
+  assert (merit["status"] == 0).all() and (filt["status"] == 0).all()
+  np.testing.assert_allclose(filt["obj"], merit["obj"], rtol=1e-8)
+  assert np.abs(filt["z"] - merit["z"]).max() <= 1e-5
+  assert filt["iters"].sum() <= 0.85 * merit["iters"].sum(), (filt["iters"].sum(), merit["iters"].sum())
+
+
 # ----------------------------------------------------------------------------- (c) solve_with_params
 def _param_system():
   from myriad_b200.systems import SystemType

@@ -10,7 +10,8 @@ for name in quads:
   tr = PR.Transcription(SystemType.CARTPOLE(), PR.TRAPEZOIDAL if name == "trap" else PR.HERMITE_SIMPSON, "HEUN", 100, 1)
   eng = Engine(tr.desc())
   for B in (1024, 4096, 8192):
-    x0 = PR.sample_x0(tr.system, B, device="cuda")
+    off = int(os.environ.get("ROW_OFFSET", "0"))   # rows [off, off + B) of the seeded draw (another rank's shard)
+    x0 = PR.sample_x0(tr.system, off + B, device="cuda")[off:].contiguous()
     z0, lb, ub = PR.build_batch(tr, x0)
     out = eng.ipm_solve(z0, lb, ub); torch.cuda.synchronize()
     best = 1e9
