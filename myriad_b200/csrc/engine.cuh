@@ -26,6 +26,7 @@ struct IpmOpts {
   int max_ls;
   int acceptable_iter;
   int use_filter;     // line search: a trial point is accepted by the l1-merit Armijo test OR by IPOPT's filter rules
+  int use_watchdog;   // after 10 shortened steps in a row: up to 3 full steps judged against the stored iterate, else roll back
   double tol, acceptable_tol;
   double mu_init, mu_min, kappa_eps, kappa_mu, theta_mu, tau_min;
   double bound_push, bound_frac, bound_relax, kappa_sigma, s_max;
@@ -114,6 +115,7 @@ struct Dims {
   X(sig, ldq * NW) X(rsl, ldq * NW) X(rsu, ldq * NW) X(dzL, ldq * NW) X(dzU, ldq * NW)                  \
   X(phi, Q * NC) X(psi, Q * NC) X(c, St * NC) X(sch, St * NC) X(ct, St * NC)                                          \
   X(dz2, ldq * NW) X(csoc, St * NC) X(dl2, St * NC)                                                                   \
+  X(wz, ldq * NW) X(wzL, ldq * NW) X(wzU, ldq * NW) X(wlam, St * NC)   /* watchdog: the stored iterate */               \
   X(ext, scheme_is_lifted<S>::value ? 6 * Q * NW + St * NC : 0)
 
 template <class S>
@@ -1454,6 +1456,20 @@ inline bool trace_enabled() { static const bool on = getenv("MYR_TRACE") != null
 __device__ __forceinline__ bool trace_enabled() { return true; }
 #endif
 
+// watchdog: store (save = true) or restore the iterate (z, lambda, z_L, z_U); out of line -- it runs once in thousands of
+// iterations and must not cost the iteration loop registers or instruction-cache footprint
+template <class S>
+MYR_HDN void watchdog_copy(const WS<S>& ws, int ncn, bool save) {
+  MYR_FOR_VARS(it) {
+    const int q = it.q, i = it.i;
+    if (save) { NQ(wz, q, i) = NQ(z, q, i); NQ(wzL, q, i) = NQ(zL, q, i); NQ(wzU, q, i) = NQ(zU, q, i); }
+    else { NQ(z, q, i) = NQ(wz, q, i); NQ(zL, q, i) = NQ(wzL, q, i); NQ(zU, q, i) = NQ(wzU, q, i); }
+  }
+  for (int k = MYR_TID; k < ncn; k += MYR_NT) {
+    if (save) ws.wlam[k] = ws.lam[k]; else ws.lam[k] = ws.wlam[k];
+  }
+}
+
 template <class S>
 MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const InstPtrs& ip, const WS<S>& ws) {
   constexpr int NW = S::NW, NC = S::NC;
@@ -1513,6 +1529,21 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
 #endif
   int nfilt = 0;
   double theta_max = -1.0, theta_min = -1.0, mu_filter = mu;
+  // Watchdog (IPOPT: watchdog_shortened_iter_trigger = 10, watchdog_trial_iter_max = 3).  A run of shortened steps can
+  // go on for hundreds of iterations when the full step is a good one that neither the merit function nor the filter's
+  // objective-type test will take (one CARTPOLE start state in 65 536: 432 iterations of 1-3 % steps, then three full
+  // steps to 1e-8).  After kWdTrigger shortened iterations in a row the iterate is stored and full steps are taken
+  // without a test; a later trial point that is acceptable RELATIVE TO THE STORED ITERATE ends the procedure, kWdMaxIter
+  // steps without one restore the stored iterate and the regular line search carries on (with a cool-down).
+  // Both safeguards (watchdog, regularised retry after a failed line search) are compiled into the plain collocation
+  // kernels only: the lifted-shooting and NODE kernels are the most register-starved ones and lost 6-12 % to the extra
+  // live state, for instance classes on which neither event has been observed.
+  constexpr bool kSafeguards = !scheme_is_lifted<S>::value && !Layout<S>::kCoopMlp;
+  constexpr int kWdTrigger = 10, kWdMaxIter = 3, kWdCooldown = 10;
+  int wd_short = 0, wd_iter = 0, wd_cool = 0;
+  double delta_force = 0.0;   // > 0: the line search of this iterate failed, factorise with at least this regularisation
+  int ls_retries = 0;
+  double wd_c1 = 0.0, wd_bphi = 0.0, wd_mu = 0.0, wd_nu = 0.0;
 
   while (true) {
     // ---------------- K1: evaluate with derivatives; rb = grad f + J^T lam
@@ -1576,7 +1607,7 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     // KKT node phase, first factorisation attempt only: kkt_factor, mu_apply)
     MYR_PH(2);
     // ---------------- K2: KKT solve with inertia correction (IPOPT Algorithm IC)
-    double delta = 0.0, dHd = 0.0;   // dHd: this thread's part of dz^T H dz, from the back-substitution
+    double delta = kSafeguards ? delta_force : 0.0, dHd = 0.0;   // dHd: this thread's part of dz^T H dz, from the back-substitution
     bool ok = false;
     for (int tries = 0; tries < 60; ++tries) {
       // accurate steps only matter near the solution: refine the linear solve in the end game only
@@ -1647,6 +1678,15 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
     bool ftype = false;
     double alpha = a_pr;
     bool accepted = false;
+    bool wd_rollback = false, wd_free = false;   // wd_free: the accepted step was a watchdog step (no filter entry for it)
+    if (kSafeguards && wd_iter > 0 && mu != wd_mu) { wd_iter = 0; wd_short = 0; }   // a barrier update ends the watchdog
+    if (kSafeguards && O.use_watchdog && wd_iter == 0 && wd_cool == 0 && wd_short >= kWdTrigger) {
+      // store the iterate and its reference values; the trial loop below then runs in watchdog mode
+      watchdog_copy<S>(ws, ncn, true);
+      wd_c1 = c1; wd_bphi = bphi0; wd_mu = mu; wd_nu = nu;
+      wd_iter = 1;
+    }
+    if (kSafeguards && wd_cool > 0) --wd_cool;
     double f_t = 0.0;
     // Armijo with IPOPT's rounding-error relaxation (10 eps |phi|) so that converged iterates are not rejected by
     // cancellation.  The infeasibility term gets its own allowance: sum |c| is a sum of differences of O(|x|) role values
@@ -1705,6 +1745,14 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
           } else if (c1_t <= (1.0 - kGammaTheta) * c1 || bphi_t <= bphi0 - kGammaPhi * c1) { accepted = true; break; }
         }
       }
+      if (kSafeguards && wd_iter > 0 && !soc && ls == 0 && isfinite(phit)) {
+        // watchdog mode and the full step failed the regular tests against the CURRENT iterate: judge it against the stored
+        // one (sufficient progress in infeasibility or barrier objective); failing that, take it anyway -- or give up
+        const double bphi_t = f_t - mu * blog;
+        if (wd_iter > 1 && (c1_t <= (1.0 - kGammaTheta) * wd_c1 || bphi_t <= wd_bphi - kGammaPhi * wd_c1)) { wd_iter = 0; wd_short = 0; accepted = true; break; }
+        if (wd_iter > kWdMaxIter) { wd_rollback = true; break; }
+        ++wd_iter; wd_free = true; accepted = true; break;
+      }
       if (!soc) {
         // second-order correction (IPOPT A-5.5 .. A-5.9): the full step was rejected without reducing the infeasibility,
         // typically because the constraint curvature along dz outweighs the predicted decrease (Maratos effect).
@@ -1727,6 +1775,12 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
         MYR_SYNC();
       }
     }
+    if (kSafeguards && wd_rollback) {   // the watchdog steps led nowhere: back to the stored iterate, regular line search from there
+      watchdog_copy<S>(ws, ncn, false);
+      nu = wd_nu; wd_iter = 0; wd_short = 0; wd_cool = kWdCooldown;
+      MYR_SYNC();
+      continue;
+    }
     const double* dl_acc = ws.dlam;
     const double* step_acc = ws.dz;
     if (accepted && soc) {  // the multiplier step of the corrected system goes with the corrected primal step
@@ -1743,7 +1797,19 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
 #define MYR_SOC_ARM_AFTER 2
 #endif
     if (hard_iters >= MYR_SOC_ARM_AFTER) soc_armed = true;
-    if (!accepted) { status = (E0 <= O.acceptable_tol) ? ST_ACCEPTABLE : ST_LINESEARCH; break; }
+    if (!accepted) {
+      // No step length was acceptable.  Far from the solution that almost always means the step is not a descent
+      // direction because the inertia test passed on rounding noise (nearly singular pivot blocks; seen on 1 of 8192
+      // Hermite-Simpson instances, and only in some builds): redo the iteration with a larger regularisation -- a few
+      // times -- before giving up.
+      if (kSafeguards && E0 > O.acceptable_tol && ls_retries < 3 && delta < O.delta_max) {
+        delta_force = fmax(delta, O.delta_0) * O.kappa_w_plus_first;
+        ++ls_retries;
+        continue;
+      }
+      status = (E0 <= O.acceptable_tol) ? ST_ACCEPTABLE : ST_LINESEARCH; break;
+    }
+    if (kSafeguards) { delta_force = 0.0; ls_retries = 0; }
 
     MYR_PH(5);
     // ---------------- accept: primal, equality multipliers, bound multipliers (with the kappa_sigma safeguard)
@@ -1763,7 +1829,11 @@ MYR_HDI InstResult ipm_solve_instance(const Problem& P, const IpmOpts& O, const 
       }
     }
     for (int k = MYR_TID; k < ncn; k += MYR_NT) ws.lam[k] += alpha * dl_acc[k];
-    if (O.use_filter && !ftype) {   // the iterate just left joins the filter (unless the step was an objective-type step)
+    if (kSafeguards) {
+      wd_short = (ls_used >= 1 && !wd_free) ? wd_short + 1 : (wd_iter > 0 ? wd_short : 0);
+      if (wd_iter > 0 && !wd_free && ls_used == 0) { wd_iter = 0; wd_short = 0; }   // a regular full step: the watchdog is done
+    }
+    if (O.use_filter && !ftype && !(kSafeguards && wd_free)) {   // the iterate just left joins the filter (unless the step was an objective-type step)
       if (MYR_TID == 0) {
         const int pos = nfilt % kFilterMax;
         filt[2 * pos] = (1.0 - kGammaTheta) * c1; filt[2 * pos + 1] = bphi0 - kGammaPhi * c1;

@@ -706,6 +706,8 @@ inline IpmOpts make_opts(const MyrIpmOpts* o) {
   r.eta = 1e-4; r.rho = 0.1;
   r.use_filter = 1;
   if (const char* e = getenv("MYR_FILTER")) r.use_filter = atoi(e) != 0;   // A/B knob: 0 = l1-merit acceptance only
+  r.use_watchdog = 1;
+  if (const char* e = getenv("MYR_WATCHDOG")) r.use_watchdog = atoi(e) != 0;
   r.delta_reg = 1e-8; r.max_refine = 1;
   r.max_soc = (o && o->max_soc != 0) ? (o->max_soc > 0 ? o->max_soc : 0) : 4;
   if (const char* e = getenv("MYR_MU_INIT")) r.mu_init = atof(e);          // tuning knobs (debug)

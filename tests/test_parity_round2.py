@@ -231,6 +231,31 @@ def test_filter_line_search_keeps_the_optima_and_cuts_iterations(monkeypatch):
   assert filt["iters"].sum() <= 0.85 * merit["iters"].sum(), (filt["iters"].sum(), merit["iters"].sum())
 
 
+def test_watchdog_ends_a_crawl_of_shortened_steps(monkeypatch):
+  """Row 56635 of the seeded CARTPOLE draw is the worst of 65 536: without the watchdog the line search accepts only
+  1-3 % steps for ~400 iterations before three full steps finish the solve.  With the watchdog (10 shortened steps in a
+  row -> up to 3 full steps judged against the stored iterate) it must reach the same optimum in a tenth of that."""
+  from myriad_b200 import problems as PR
+  tr = product_transcription("c2_cartpole_trap_100")
+  fx = load("c2_cartpole_trap_100")
+  x0 = PR.sample_x0(tr.system, 56636).numpy()[56635]
+  z0 = fx["guess"].copy()[None]; lb = fx["bounds"][:, 0].copy()[None]; ub = fx["bounds"][:, 1].copy()[None]
+  n, L = tr.n, tr.nx_nodes
+  xT = np.asarray(tr.system.x_T, dtype=np.float64)
+  xg = x0[None, :] + np.arange(L, dtype=np.float64)[:, None] * ((xT - x0) / (L - 1))[None, :]
+  xg[-1] = xT
+  z0[0, :L * n] = xg.reshape(-1)
+  lb[0, :n] = x0; ub[0, :n] = x0
+  host = _Host()
+  monkeypatch.setenv("MYR_WATCHDOG", "0")
+  crawl = host.solve(tr, z0, lb, ub)
+  monkeypatch.setenv("MYR_WATCHDOG", "1")
+  wd = host.solve(tr, z0, lb, ub)
+  assert crawl["status"][0] == 0 and wd["status"][0] == 0
+  assert crawl["iters"][0] > 200 and wd["iters"][0] <= 60, (crawl["iters"], wd["iters"])
+  np.testing.assert_allclose(wd["obj"], crawl["obj"], rtol=1e-8)
+
+
 # ----------------------------------------------------------------------------- (c) solve_with_params
 def _param_system():
   from myriad_b200.systems import SystemType

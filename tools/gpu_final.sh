@@ -15,4 +15,4 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 for tool in racecheck memcheck synccheck; do
   timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_run.py > gpurun_out/r2_sanitizer_$tool.log 2>&1; echo "$tool rc=$?" >> gpurun_out/r2_sanitizer_$tool.log; tail -2 gpurun_out/r2_sanitizer_$tool.log
 done
-ls -la gpurun_out/*.ncu-rep | tail -4
+ls -la gpurun_out/*.ncu-rep | tail -4; python tools/hs_fail_debug.py hs 8192 > gpurun_out/r2_hs_B8192_status.log 2>&1; tail -2 gpurun_out/r2_hs_B8192_status.log
