@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MYR_ABI_VERSION 3
+#define MYR_ABI_VERSION 4
 #define MYR_MAX_PARAMS 16
 #define MYR_MAX_NODE_LAYERS 5   /* Linear layers of a NODE MLP: up to 4 hidden + the output layer */
 #define MYR_MAX_NODE_WIDTH 128  /* widest hidden layer */
@@ -198,6 +198,33 @@ int myr_dynamics(const MyrDesc* desc, int B, const double* x, const double* u, c
  * (myriad/nlp_solvers/extra_gradient.py:21-33).  Works for all three transcriptions. */
 int myr_jtvec(const MyrDesc* desc, int B, const double* Jblk, const double* lam, double* out, void* stream);
 
+/* Options of the forward-backward sweep; zero / negative fields take the reference's values. */
+typedef struct MyrFbsmOpts {
+  int32_t max_iter;    /* sweeps per fixed-point solve; the reference loops without a cap; default 10000 */
+  int32_t max_secant;  /* secant steps on the free terminal adjoint; default 100 */
+  int32_t term_state;  /* index of the ONE state with a terminal value (system.x_T[i] is not None), or -1: none
+                        * (forward_backward_sweep.py:59-70) */
+  int32_t reserved;
+  double delta;        /* stopping_criterion's delta (trajectory_optimizers/base.py:129); default 1e-3 */
+  double secant_tol;   /* |x_T - target| at which the secant iteration stops (forward_backward_sweep.py:137); default 1e-10 */
+  double term_value;   /* the terminal value of state term_state */
+  double guess_a, guess_b; /* system.guess_a / guess_b: the two starting values of the secant iteration */
+} MyrFbsmOpts;
+
+/* Indirect optimizer: the Forward-Backward Sweep Method for B start states in one launch, one thread per instance.
+ * Replaces FBSM.solve / sequencesolver (myriad/trajectory_optimizers/forward_backward_sweep.py:88-158) with its RK4 sweeps
+ * (integrate_fbsm, myriad/utils.py:138-197), the systems' adj_ODE / optim_characterization (myriad/systems/lenhart) and
+ * the stopping rule (trajectory_optimizers/base.py:128-141).  desc: system_id, intervals = hp.fbsm_intervals, T, params
+ * (the other fields are ignored).  x0: [B][n] DEVICE.  adj_T: [n] HOST, system.adj_T, or NULL (zeros).  char_lb / char_ub:
+ * [m] HOST, the bounds row(s) the system's optim_characterization clamps with.
+ * Outputs (DEVICE) are TIME-MAJOR with the instance index fastest -- x: [N+1][n][B], u: [N+1][m][B], adj: [N+1][n][B] --
+ * unlike the instance-major convention of the other calls: they are the sweep's working storage and this is the layout
+ * in which a warp's accesses coalesce.  iters: [B] sweeps performed; status: [B] MYR_ST_SOLVED / MYR_ST_MAXITER / MYR_ST_NAN.
+ * Systems: the 13 continuous Lenhart members of SystemType; others return MYR_E_UNSUPPORTED. */
+int myr_fbsm_solve(const MyrDesc* desc, const MyrFbsmOpts* opts, int B, const double* x0, const double* adj_T,
+                   const double* char_lb, const double* char_ub, double* x, double* u, double* adj,
+                   int32_t* iters, int32_t* status, void* stream);
+
 /* Registers a system that was compiled into its own shared library (myriad_b200/plugin.py builds it from symbolic
  * dynamics / cost with the same generator and kernel templates as the built-in systems).  vtable: the pointer returned by
  * the plugin library's myr_vtable_<Sys>() export; its id must be >= MYR_SYS_USER_BASE.  Replaces subclassing
@@ -226,6 +253,9 @@ int myr_host_rollout_cost(const MyrDesc* desc, int B, int nu_rows, const double*
 int myr_host_dynamics(const MyrDesc* desc, int B, const double* x, const double* u, const double* t,
                       double* f, double* g);
 int myr_host_jtvec(const MyrDesc* desc, int B, const double* Jblk, const double* lam, double* out);
+int myr_host_fbsm_solve(const MyrDesc* desc, const MyrFbsmOpts* opts, int B, const double* x0, const double* adj_T,
+                        const double* char_lb, const double* char_ub, double* x, double* u, double* adj,
+                        int32_t* iters, int32_t* status);
 
 #ifdef __cplusplus
 }

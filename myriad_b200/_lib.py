@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MYR_LIB", os.path.join(HERE, "libmyriad_b200.so"))  # MYR_LIB: A/B builds of the same ABI
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 WS_HEADER = 16  # MYR_WS_HEADER
 MAX_PARAMS = 16
 MAX_NODE_LAYERS = 5
@@ -51,6 +51,12 @@ class MyrIpmOpts(C.Structure):
               ("tol", C.c_double), ("acceptable_tol", C.c_double), ("mu_init", C.c_double)]
 
 
+class MyrFbsmOpts(C.Structure):
+  _fields_ = [("max_iter", C.c_int32), ("max_secant", C.c_int32), ("term_state", C.c_int32), ("reserved", C.c_int32),
+              ("delta", C.c_double), ("secant_tol", C.c_double), ("term_value", C.c_double),
+              ("guess_a", C.c_double), ("guess_b", C.c_double)]
+
+
 class MyriadError(RuntimeError):
   pass
 
@@ -60,7 +66,7 @@ _lib = None
 
 EXPORTS = ["myr_abi_version", "myr_last_error", "myr_problem_sizes", "myr_eval", "myr_kkt_solve", "myr_ipm_solve",
            "myr_rollout_cost", "myr_dynamics", "myr_jtvec", "myr_register_system", "myr_bench_dfma", "myr_host_eval", "myr_host_kkt_solve", "myr_host_ipm_solve",
-           "myr_host_rollout_cost", "myr_host_dynamics", "myr_host_jtvec"]
+           "myr_host_rollout_cost", "myr_host_dynamics", "myr_host_jtvec", "myr_fbsm_solve", "myr_host_fbsm_solve"]
 
 
 def lib() -> C.CDLL:
@@ -92,6 +98,9 @@ def lib() -> C.CDLL:
   jt = [C.POINTER(MyrDesc), C.c_int, _P, _P, _P]
   L.myr_jtvec.argtypes = jt + [_P]
   L.myr_host_jtvec.argtypes = jt
+  fb = [C.POINTER(MyrDesc), C.POINTER(MyrFbsmOpts), C.c_int] + [_P] * 9
+  L.myr_fbsm_solve.argtypes = fb + [_P]
+  L.myr_host_fbsm_solve.argtypes = fb
   L.myr_register_system.argtypes = [_P]
   L.myr_bench_dfma.argtypes = [C.c_int, C.c_int, _P, _P]
   for name in EXPORTS:

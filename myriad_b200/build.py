@@ -71,7 +71,7 @@ def build(force: bool = False, systems=None, jobs: int | None = None, verbose: b
     if s not in gen:
       raise KeyError(f"system {s} has no generated device code (tools/gen_systems.py)")
   src_t = _newest_source()
-  sys_src_t = _newest_source(exclude=("api.cu",))  # the per-system units do not include the dispatcher
+  sys_src_t = _newest_source(exclude=("api.cu", "fbsm.cu", "fbsm.cuh"))  # the per-system units include neither
   tag = "_".join(sorted(names)) + "|node:" + "_".join(sorted(s for s in NODE_SYSTEMS if s in names))
   stamp = os.path.join(BUILD, "systems.txt")
   prev = open(stamp).read() if os.path.exists(stamp) else ""
@@ -96,6 +96,12 @@ def build(force: bool = False, systems=None, jobs: int | None = None, verbose: b
   objs.append(api_obj)
   if force or not os.path.exists(api_obj) or os.path.getmtime(api_obj) < src_t or prev != tag:
     tasks.append(("api", [nvcc, *flags, xmacro, xmacro_node, "-c", os.path.join(CSRC, "api.cu"), "-o", api_obj]))
+  fbsm_obj = os.path.join(BUILD, "fbsm.o")  # forward-backward sweep: needs only the generated systems
+  objs.append(fbsm_obj)
+  fbsm_t = max(os.path.getmtime(os.path.join(CSRC, f)) for f in ("fbsm.cu", "fbsm.cuh", "systems_gen.cuh"))
+  fbsm_t = max(fbsm_t, os.path.getmtime(os.path.join(ROOT, "include", "myriad_b200.h")))
+  if force or not os.path.exists(fbsm_obj) or os.path.getmtime(fbsm_obj) < fbsm_t:
+    tasks.append(("fbsm", [nvcc, *flags, "-c", os.path.join(CSRC, "fbsm.cu"), "-o", fbsm_obj]))
   if tasks:
     if verbose:
       print(f"[myriad_b200.build] compiling {len(tasks)} unit(s) with {jobs} job(s): {[t[0] for t in tasks]}", flush=True)

@@ -162,6 +162,7 @@ class PredatorPrey(FiniteHorizonControlSystem):
     super().__init__(x_0=np.array([x_0[0], x_0[1], x_0[2]], dtype=np.float64), x_T=[None, None, B], T=T,
                      bounds=np.array([[0., 11.], [0., 11.], [0., 5.], [0., M]]), terminal_cost=True, discrete=False,
                      device_name="PREDATORPREY", params=[d_1, d_2, A])
+    self.guess_a, self.guess_b = guess_a, guess_b  # secant start values of the FBSM (predator_prey.py:75-77)
 
   def terminal_cost_fn(self, x_T, u_T, T=None):
     return x_T[0]

@@ -40,7 +40,8 @@ def get_optimizer(hp: HParams, cfg: Config, system) -> TrajectoryOptimizer:
   elif hp.optimizer == OptimizerType.SHOOTING:
     optimizer = MultipleShootingOptimizer(hp, cfg, system)
   elif hp.optimizer == OptimizerType.FBSM:
-    raise NotImplementedError("FBSM (indirect method) is outside the B200 hot path; see DESIGN.md")
+    from myriad_b200.trajectory_optimizers.fbsm import FBSM
+    optimizer = FBSM(hp, cfg, system)
   else:
     raise KeyError
   return optimizer

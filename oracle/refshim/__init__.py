@@ -47,6 +47,21 @@ class ClampArray(np.ndarray):
       idx = self.shape[0] - 1
     return super().__getitem__(idx)
 
+  @property
+  def at(self):
+    """jnp's functional update ``a.at[idx].set(v)`` (forward_backward_sweep.py:89): returns an updated copy"""
+    arr = self
+
+    class _At:
+      def __getitem__(self, idx):
+        class _Setter:
+          def set(self, v):
+            out = np.array(arr)
+            out[idx] = v
+            return _wrap(out)
+        return _Setter()
+    return _At()
+
   def __iter__(self):  # iteration must still stop at the end
     for i in range(self.shape[0]):
       v = super().__getitem__(i)
