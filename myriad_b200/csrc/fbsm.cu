@@ -11,8 +11,12 @@ namespace myr {
 int fail(int code, const char* fmt, const char* a = "", long long v = 0);  // api.cu
 double system_default_T(int id);                                           // api.cu
 
+// One warp per CTA: a warp is the unit that runs until its slowest instance has converged, registers (not the CTA count)
+// bound the occupancy, and 32-thread CTAs spread a small batch over 4x as many SMs as 128-thread ones would.
+constexpr int kFbsmThreads = 32;
+
 template <class Sys>
-__global__ void __launch_bounds__(128) fbsm_kernel(const __grid_constant__ FbsmParams P) {
+__global__ void __launch_bounds__(kFbsmThreads) fbsm_kernel(const __grid_constant__ FbsmParams P) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
   FbsmInstance<Sys>(P, b).run();
@@ -54,7 +58,7 @@ static int fbsm_run(const MyrDesc* d, const MyrFbsmOpts* o, int B, const double*
     for (int b = 0; b < B; ++b) FbsmInstance<Sys>(P, b).run();
     return MYR_OK;
   }
-  const int threads = 128;  // 148 SMs x 16 resident CTAs of 128 threads cover 303 104 instances per wave
+  const int threads = kFbsmThreads;
   fbsm_kernel<Sys><<<(B + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MYR_E_CUDA, "fbsm_kernel launch: %s", cudaGetErrorString(e));

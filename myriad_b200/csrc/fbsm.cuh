@@ -306,11 +306,20 @@ struct FbsmInstance {
       for (int k = 0; k < m; ++k) su[k] = du[k] = 0.0;
       double xc[n], uc[m], un[m], um[m], k1[n], k2[n], k3[n], k4[n], w[n], xo[n];
       // ---- forward sweep of the states (utils.py:166-176 with h > 0)
+      // Loads run ONE STEP AHEAD of their use (un2 / xo2 / xp2 ...): the addresses depend only on the step index, and the
+      // compiler may not hoist them over the stores itself, so each thread keeps the next step's operands in flight while
+      // it works through the current step's dependent RK4 chain.
+      double un2[m] = {}, xo2[n] = {};
       load(P.x, 0, n, xc);
       load(P.u, 0, m, uc);
+      load(P.u, 1, m, un);
+      load(P.x, 1, n, xo);
       for (int k = 0; k < n; ++k) sx[k] += fabs(xc[k]);
       for (int i = 0; i < N; ++i) {
-        load(P.u, i + 1, m, un);
+        if (i + 1 < N) {
+          load(P.u, i + 2, m, un2);
+          load(P.x, i + 2, n, xo2);
+        }
         for (int k = 0; k < m; ++k) um[k] = (uc[k] + un[k]) / 2.0;
         Sys::f(xc, uc, P.p, k1);
         for (int k = 0; k < n; ++k) w[k] = xc[k] + h * k1[k] / 2.0;
@@ -319,14 +328,14 @@ struct FbsmInstance {
         Sys::f(w, um, P.p, k3);
         for (int k = 0; k < n; ++k) w[k] = xc[k] + h * k3[k];
         Sys::f(w, un, P.p, k4);
-        load(P.x, i + 1, n, xo);
         for (int k = 0; k < n; ++k) {
           xc[k] = xc[k] + (h / 6.0) * (k1[k] + 2.0 * k2[k] + 2.0 * k3[k] + k4[k]);
           sx[k] += fabs(xc[k]);
           dx[k] += fabs(xc[k] - xo[k]);
+          xo[k] = xo2[k];
         }
         store(P.x, i + 1, n, xc);
-        for (int k = 0; k < m; ++k) uc[k] = un[k];
+        for (int k = 0; k < m; ++k) { uc[k] = un[k]; un[k] = un2[k]; }
       }
       // ---- backward sweep of the adjoints (h < 0) with the control update fused in
       const double hb = -h;
@@ -334,10 +343,17 @@ struct FbsmInstance {
       load(P.adj, N, n, ac);  // terminal condition: never changes
       for (int k = 0; k < n; ++k) sa[k] += fabs(ac[k]);
       // xc == x[N], uc == u[N] (old) at this point
+      double xp2[n] = {}, up2[m] = {}, ao2[n] = {};
+      load(P.x, N - 1, n, xp);
+      load(P.u, N - 1, m, up);
+      load(P.adj, N - 1, n, ao);
       for (int i = N; i >= 1; --i) {
         const double t = time_at(i);
-        load(P.x, i - 1, n, xp);
-        load(P.u, i - 1, m, up);
+        if (i >= 2) {
+          load(P.x, i - 2, n, xp2);
+          load(P.u, i - 2, m, up2);
+          load(P.adj, i - 2, n, ao2);
+        }
         for (int k = 0; k < n; ++k) xm[k] = (xc[k] + xp[k]) / 2.0;
         for (int k = 0; k < m; ++k) um[k] = (uc[k] + up[k]) / 2.0;
         Ind::adj(ac, xc, uc, t, P.p, k1);
@@ -356,15 +372,16 @@ struct FbsmInstance {
           ue[k] = v;
         }
         store(P.u, i, m, ue);
-        load(P.adj, i - 1, n, ao);
         for (int k = 0; k < n; ++k) {
           ac[k] = ac[k] + (hb / 6.0) * (k1[k] + 2.0 * k2[k] + 2.0 * k3[k] + k4[k]);
           sa[k] += fabs(ac[k]);
           da[k] += fabs(ac[k] - ao[k]);
           xc[k] = xp[k];
+          xp[k] = xp2[k];
+          ao[k] = ao2[k];
         }
         store(P.adj, i - 1, n, ac);
-        for (int k = 0; k < m; ++k) uc[k] = up[k];
+        for (int k = 0; k < m; ++k) { uc[k] = up[k]; up[k] = up2[k]; }
       }
       Ind::opt(ac, xc, time_at(0), P.p, P.lb, P.ub, ue);
       for (int k = 0; k < m; ++k) {

@@ -45,6 +45,22 @@ def run(name, N, B, reps=3):
         f"solved {(st == 0).sum()}/{B}; algorithmic {bytes_alg / 1e9:.2f} GB -> {bytes_alg / t / 1e6:.0f} GB/s = "
         f"{bytes_alg / t / 1e6 / pk:.3f} of {pk:.0f} ({src})", flush=True)
 
+def cpu_lines(name, N, B):
+  """same sweep templates on the host cores (OpenMP over instances) and the NumPy oracle on one core, bounded samples"""
+  from oracle import fbsm as OF
+  hp = HParams(system=SystemType[name], optimizer=OptimizerType.FBSM, fbsm_intervals=N)
+  opt = get_optimizer(hp, Config(verbose=False, plot=False), hp.system())
+  rng = np.random.Generator(np.random.PCG64(3))
+  x0d = np.asarray(opt.system.x_0, dtype=np.float64)
+  x0 = x0d * (1 + 0.1 * rng.uniform(-1, 1, size=(B, x0d.shape[0])))
+  t = time.time(); r = opt.host_solve_batch(x0); dt = time.time() - t
+  print(f"FBSM {name} N={N}: host build of the same templates, {os.cpu_count()} cores, {B} instances: {dt:.2f} s -> {B / dt:.0f} solves/s", flush=True)
+  t = time.time(); k = 0
+  while time.time() - t < 10 and k < 8:
+    OF.solve(name, N, x0[k]); k += 1
+  dt = time.time() - t
+  print(f"FBSM {name} N={N}: NumPy oracle (the reference's algorithm as the reference runs it, one core), {k} instances: {dt / k:.2f} s per solve -> {k / dt:.2f} solves/s", flush=True)
+
 if __name__ == "__main__":
   if len(sys.argv) > 1 and sys.argv[1] == "profile":
     run(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), reps=1)
@@ -55,3 +71,4 @@ if __name__ == "__main__":
     run("HIVTREATMENT", 1000, 65536)
     run("BEARPOPULATIONS", 1000, 65536)
     run("PREDATORPREY", 1000, 16384)
+    cpu_lines("CANCERTREATMENT", 1000, 2048)
