@@ -62,6 +62,7 @@ enum {
   MYR_SYS_ROCKETLANDING = 17,
   MYR_SYS_PENDULUM = 18,     /* non-smooth: clip / angle_normalize with JAX's sub-gradient choices */
   MYR_SYS_MOUNTAINCAR = 19,  /* non-smooth: clipped force */
+  MYR_SYS_INVASIVEPLANT = 20, /* DISCRETE dynamics: myr_fbsm_solve only (the reference's direct optimizers reject it too) */
   /* NodeSystem (myriad/systems/neural_ode/node_system.py:14-42) wrapping true system k: id = MYR_SYS_NODE_BASE + k.
    * Dynamics = the NODE MLP of myriad/neural_ode/create_node.py:110-117 (weights in MyrDesc.theta); cost, bounds,
    * horizon and the verification rollout are the true system's. */
@@ -220,7 +221,8 @@ typedef struct MyrFbsmOpts {
  * Outputs (DEVICE) are TIME-MAJOR with the instance index fastest -- x: [N+1][n][B], u: [N+1][m][B], adj: [N+1][n][B] --
  * unlike the instance-major convention of the other calls: they are the sweep's working storage and this is the layout
  * in which a warp's accesses coalesce.  iters: [B] sweeps performed; status: [B] MYR_ST_SOLVED / MYR_ST_MAXITER / MYR_ST_NAN.
- * Systems: the 13 continuous Lenhart members of SystemType; others return MYR_E_UNSUPPORTED. */
+ * Systems: the 14 indirect (Lenhart) members of SystemType; others return MYR_E_UNSUPPORTED.  For the discrete one
+ * (INVASIVEPLANT) intervals must equal T (h = 1) and u has N rows: u: [N][m][B]. */
 int myr_fbsm_solve(const MyrDesc* desc, const MyrFbsmOpts* opts, int B, const double* x0, const double* adj_T,
                    const double* char_lb, const double* char_ub, double* x, double* u, double* adj,
                    int32_t* iters, int32_t* status, void* stream);

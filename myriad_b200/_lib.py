@@ -20,7 +20,7 @@ NODE_BASE = 100
 SYSTEM_IDS = {
   "SIMPLECASE": 0, "CARTPOLE": 1, "VANDERPOL": 2, "CANCERTREATMENT": 3, "MOULDFUNGICIDE": 4, "BIOREACTOR": 5,
   "SIMPLECASEWITHBOUNDS": 6, "GLUCOSE": 7, "HARVEST": 8, "TIMBERHARVEST": 9, "SEIR": 10, "EPIDEMICSEIRN": 11, "HIVTREATMENT": 12, "BACTERIA": 13, "TUMOUR": 14, "PREDATORPREY": 15, "BEARPOPULATIONS": 16,
-  "ROCKETLANDING": 17, "PENDULUM": 18, "MOUNTAINCAR": 19,
+  "ROCKETLANDING": 17, "PENDULUM": 18, "MOUNTAINCAR": 19, "INVASIVEPLANT": 20,
 }
 OPT_SHOOTING, OPT_TRAPEZOIDAL, OPT_HERMITE_SIMPSON = 0, 1, 2
 METHOD_IDS = {"EULER": 0, "HEUN": 1, "MIDPOINT": 2, "RK4": 3}

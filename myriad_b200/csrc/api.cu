@@ -37,6 +37,7 @@ double system_default_T(int id) {
     case MYR_SYS_ROCKETLANDING: return 16.0;
     case MYR_SYS_PENDULUM: return 15.0;
     case MYR_SYS_MOUNTAINCAR: return 300.0;
+    case MYR_SYS_INVASIVEPLANT: return 10.0;
     default: return 1.0;
   }
 }

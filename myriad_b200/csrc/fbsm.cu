@@ -33,6 +33,8 @@ static int fbsm_run(const MyrDesc* d, const MyrFbsmOpts* o, int B, const double*
   P.B = B;
   P.N = d->intervals;
   P.T = d->T > 0 ? d->T : system_default_T(Sys::id);
+  if (Indirect<Sys>::discrete && (double)P.N != P.T)  // forward_backward_sweep.py:33-35: N = int(T), h = 1
+    return fail(MYR_E_BADARG, "discrete system %s: intervals must equal T (%lld given)", Sys::name, P.N);
   P.delta = (o && o->delta > 0) ? o->delta : 1e-3;             // stopping_criterion's default delta (base.py:129)
   P.secant_tol = (o && o->secant_tol > 0) ? o->secant_tol : 1e-10;  // forward_backward_sweep.py:137
   P.max_iter = (o && o->max_iter > 0) ? o->max_iter : 10000;
@@ -84,6 +86,7 @@ static int fbsm_dispatch(const MyrDesc* d, const MyrFbsmOpts* o, int B, const do
     MYR_FBSM_CASE(SysBacteria)
     MYR_FBSM_CASE(SysPredatorprey)
     MYR_FBSM_CASE(SysBearpopulations)
+    MYR_FBSM_CASE(SysInvasiveplant)
     default:
       return fail(MYR_E_UNSUPPORTED, "FBSM needs a system with adj_ODE / optim_characterization (system_id %s%lld has none)", "",
                   d->system_id);

@@ -36,6 +36,7 @@ MYR_HD double fbsm_sign(double v) { return v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0
 template <class Sys>
 struct Indirect {
   static constexpr bool available = false;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double*, const double*, const double*, double, const double*, double*) {}
   MYR_HD static void opt(const double*, const double*, double, const double*, const double*, const double*, double*) {}
 };
@@ -44,6 +45,7 @@ struct Indirect {
 template <>
 struct Indirect<SysSimplecase> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)u; (void)t;
     o[0] = -p[0] + x[0] * a[0];
@@ -58,6 +60,7 @@ struct Indirect<SysSimplecase> {
 template <>
 struct Indirect<SysSimplecasewithbounds> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)u; (void)t;
     o[0] = -p[0] + x[0] * a[0];
@@ -72,6 +75,7 @@ struct Indirect<SysSimplecasewithbounds> {
 template <>
 struct Indirect<SysCancertreatment> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)t;
     o[0] = a[0] * (p[0] + p[2] * u[0] - p[0] * log(1.0 / x[0])) - 2.0 * p[1] * x[0];
@@ -86,6 +90,7 @@ struct Indirect<SysCancertreatment> {
 template <>
 struct Indirect<SysMouldfungicide> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)t;
     o[0] = a[0] * (p[0] + u[0]) - 2.0 * p[2] * x[0];
@@ -100,6 +105,7 @@ struct Indirect<SysMouldfungicide> {
 template <>
 struct Indirect<SysBioreactor> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)t;
     o[0] = -p[0] - p[1] * u[0] * a[0] + 2.0 * p[2] * x[0] * a[0];
@@ -116,6 +122,7 @@ struct Indirect<SysBioreactor> {
 template <>
 struct Indirect<SysGlucose> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)u; (void)t;
     o[0] = -2.0 * p[3] * (x[0] - p[4]) + a[0] * p[0];
@@ -131,6 +138,7 @@ struct Indirect<SysGlucose> {
 template <>
 struct Indirect<SysHarvest> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)x;
     o[0] = a[0] * (p[2] + u[0]) - p[0] * (p[1] * t / (t + 1.0)) * u[0];
@@ -144,6 +152,7 @@ struct Indirect<SysHarvest> {
 template <>
 struct Indirect<SysTimberharvest> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)x;
     const double e = exp(-p[0] * t);
@@ -160,6 +169,7 @@ struct Indirect<SysTimberharvest> {
 template <>
 struct Indirect<SysEpidemicseirn> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)t;
     const double A = p[0], b = p[1], d = p[2], c = p[3], e = p[4], g = p[5], al = p[6];
@@ -178,6 +188,7 @@ struct Indirect<SysEpidemicseirn> {
 template <>
 struct Indirect<SysHivtreatment> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)t;
     const double s = p[0], m1 = p[1], m2 = p[2], m3 = p[3], r = p[4], Tm = p[5], k = p[6], N = p[7], A = p[8];
@@ -195,6 +206,7 @@ struct Indirect<SysHivtreatment> {
 template <>
 struct Indirect<SysBacteria> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)t;
     o[0] = -a[0] * (p[0] + p[1] * u[0] + p[2] * u[0] * u[0] * exp(-x[0]));
@@ -209,6 +221,7 @@ struct Indirect<SysBacteria> {
 template <>
 struct Indirect<SysPredatorprey> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)t;
     o[0] = a[0] * (x[1] - 1.0 + p[0] * u[0]) - a[1] * x[1];
@@ -225,6 +238,7 @@ struct Indirect<SysPredatorprey> {
 template <>
 struct Indirect<SysBearpopulations> {
   static constexpr bool available = true;
+  static constexpr bool discrete = false;
   MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
     (void)t;
     const double r = p[0], K = p[1], mp = p[2], mf = p[3];
@@ -242,6 +256,33 @@ struct Indirect<SysBearpopulations> {
   }
 };
 
+// INVASIVEPLANT (invasive_plant.py:38-101): the one DISCRETE member of SystemType -- x_{t+1} = f(x_t, u_t), five foci with one
+// control each.  The reference accepts it only in the FBSM (the direct optimizers raise, trajectory_optimizers/base.py:66-67),
+// so it has no generated NLP code: its map lives here.  p = B, k, eps.
+struct SysInvasiveplant {
+  static constexpr int id = MYR_SYS_INVASIVEPLANT, n = 5, m = 5, nw = 10, np = 3;
+  static constexpr const char* name = "INVASIVEPLANT";
+  MYR_HD static void default_params(double* p) { p[0] = 1.0; p[1] = 1.0; p[2] = 0.01; }
+  MYR_HD static void f(const double* x, const double* u, const double* p, double* o) {  // next state, invasive_plant.py:71-72
+    for (int k = 0; k < n; ++k) o[k] = (x[k] + x[k] * p[1] / (p[2] + x[k])) * (1.0 - u[k]);
+  }
+};
+template <>
+struct Indirect<SysInvasiveplant> {
+  static constexpr bool available = true;
+  static constexpr bool discrete = true;
+  // previous adjoint (invasive_plant.py:79-82)
+  MYR_HD static void adj(const double* a, const double* x, const double* u, double t, const double* p, double* o) {
+    (void)t;
+    for (int k = 0; k < 5; ++k) o[k] = a[k] * (1.0 - u[k]) * (1.0 + p[2] * p[1] / ((p[2] + x[k]) * (p[2] + x[k])));
+  }
+  // one row of optim_characterization (invasive_plant.py:84-90): a = adj[i + 1], x = x[i]; every control clamps with the LAST row
+  MYR_HD static void opt(const double* a, const double* x, double t, const double* p, const double* lb, const double* ub, double* o) {
+    (void)t;
+    for (int k = 0; k < 5; ++k) o[k] = fbsm_clamp(0.5 * a[k] / p[0] * (x[k] + x[k] * p[1] / (p[2] + x[k])), lb[0], ub[0]);
+  }
+};
+
 // ------------------------------------------------------------------------------------------------------------------
 struct FbsmParams {
   int B, N;
@@ -254,7 +295,7 @@ struct FbsmParams {
   double lb[4], ub[4];
   const double* x0;  // [B][n]
   double* x;         // [N+1][n][B]
-  double* u;         // [N+1][m][B]
+  double* u;         // [N+1][m][B]  (discrete systems: [N][m][B], forward_backward_sweep.py:37-38)
   double* adj;       // [N+1][n][B]
   int32_t* iters;    // [B] sweeps performed (summed over the secant solves)
   int32_t* status;   // [B] MYR_ST_SOLVED / MYR_ST_MAXITER / MYR_ST_NAN
@@ -286,11 +327,54 @@ struct FbsmInstance {
     for (int k = 0; k < n; ++k) v[k] = P.x0[b * n + k];
     store(P.x, 0, n, v);
     for (int i = 1; i <= P.N; ++i) store(P.x, i, n, z);
-    for (int i = 0; i <= P.N; ++i) store(P.u, i, m, z);
+    for (int i = 0; i < P.N + (Ind::discrete ? 0 : 1); ++i) store(P.u, i, m, z);
     for (int i = 0; i < P.N; ++i) store(P.adj, i, n, z);
     for (int k = 0; k < n; ++k) v[k] = P.adj_T[k];
     if (with_a) v[P.term_state] = a;
     store(P.adj, P.N, n, v);
+  }
+
+  // One sweep of a DISCRETE system (integrate_fbsm's ``discrete`` branches, utils.py:182-186): x[i+1] = f(x[i], u[i]);
+  // adj[i-1] = adj_ODE(adj[i], x[i], u[i-1], t[i-1]); u[i] <- (u*(adj[i+1], x[i]) + u[i]) / 2 for i < N (u has N rows).
+  MYR_HD void sweep_discrete(double* sx, double* dx, double* sa, double* da, double* su, double* du) const {
+    const int N = P.N;
+    double xc[n], xn[n], xo[n], uc[m], ue[m], ac[n], an[n], ao[n], xp[n];
+    load(P.x, 0, n, xc);
+    for (int k = 0; k < n; ++k) sx[k] += fabs(xc[k]);
+    for (int i = 0; i < N; ++i) {
+      load(P.u, i, m, uc);
+      Sys::f(xc, uc, P.p, xn);
+      load(P.x, i + 1, n, xo);
+      for (int k = 0; k < n; ++k) {
+        xc[k] = xn[k];
+        sx[k] += fabs(xc[k]);
+        dx[k] += fabs(xc[k] - xo[k]);
+      }
+      store(P.x, i + 1, n, xc);
+    }
+    load(P.adj, N, n, ac);
+    for (int k = 0; k < n; ++k) sa[k] += fabs(ac[k]);
+    for (int i = N; i >= 1; --i) {  // xc == x[i]
+      load(P.u, i - 1, m, uc);
+      load(P.x, i - 1, n, xp);
+      Ind::adj(ac, xc, uc, time_at(i - 1), P.p, an);
+      Ind::opt(ac, xp, time_at(i - 1), P.p, P.lb, P.ub, ue);  // adj[i] is final; this step is the last reader of the old u[i-1]
+      for (int k = 0; k < m; ++k) {
+        const double v = 0.5 * (ue[k] + uc[k]);
+        su[k] += fabs(v);
+        du[k] += fabs(v - uc[k]);
+        ue[k] = v;
+      }
+      store(P.u, i - 1, m, ue);
+      load(P.adj, i - 1, n, ao);
+      for (int k = 0; k < n; ++k) {
+        ac[k] = an[k];
+        sa[k] += fabs(ac[k]);
+        da[k] += fabs(ac[k] - ao[k]);
+        xc[k] = xp[k];
+      }
+      store(P.adj, i - 1, n, ac);
+    }
   }
 
   // the while loop of solve(), forward_backward_sweep.py:94-110; returns the number of sweeps, sets nan_seen
@@ -304,6 +388,9 @@ struct FbsmInstance {
       double sx[n], dx[n], sa[n], da[n], su[m], du[m];
       for (int k = 0; k < n; ++k) sx[k] = dx[k] = sa[k] = da[k] = 0.0;
       for (int k = 0; k < m; ++k) su[k] = du[k] = 0.0;
+      if constexpr (Ind::discrete) {
+        sweep_discrete(sx, dx, sa, da, su, du);
+      } else {
       double xc[n], uc[m], un[m], um[m], k1[n], k2[n], k3[n], k4[n], w[n], xo[n];
       // ---- forward sweep of the states (utils.py:166-176 with h > 0)
       // Loads run ONE STEP AHEAD of their use (un2 / xo2 / xp2 ...): the addresses depend only on the step index, and the
@@ -391,6 +478,7 @@ struct FbsmInstance {
         ue[k] = v;
       }
       store(P.u, 0, m, ue);
+      }  // continuous
       ++it;
       // ---- stopping rule (base.py:128-141): continue while min(|v| sum * delta - |v - old| sum) < 0
       double mn = INFINITY;

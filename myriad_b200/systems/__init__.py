@@ -274,6 +274,18 @@ def mlp_layers(params):
   return out
 
 
+class InvasivePlant(FiniteHorizonControlSystem):
+  """myriad/systems/lenhart/invasive_plant.py:38-101: the one DISCRETE system (x_{t+1} = f(x_t, u_t), five foci, one control
+  each).  Like in the reference it works with the FBSM only -- the direct optimizers raise (trajectory_optimizers/base.py:66-67);
+  its map, previous-adjoint rule and characterisation live in csrc/fbsm.cuh."""
+
+  def __init__(self, B=1., k=1., eps=.01, x_0=(.5, 1., 1.5, 2., 10.), T=10.):
+    inf = np.inf
+    super().__init__(x_0=np.array(x_0, dtype=np.float64), x_T=None, T=T,
+                     bounds=np.array([[-inf, inf]] * 5 + [[0., 1.]] * 5), terminal_cost=False, discrete=True,
+                     device_name="INVASIVEPLANT", params=[B, k, eps])
+
+
 class _NotOnDevice:
   def __init__(self, name):
     self.name = name
@@ -304,7 +316,7 @@ class SystemType(Enum):
   TIMBERHARVEST = TimberHarvest
   BIOREACTOR = Bioreactor
   PREDATORPREY = PredatorPrey
-  INVASIVEPLANT = _NotOnDevice("INVASIVEPLANT")
+  INVASIVEPLANT = InvasivePlant
   ROCKETLANDING = RocketLanding
 
   def __call__(self, *args, **kwargs) -> FiniteHorizonControlSystem:

@@ -34,6 +34,7 @@ INDIRECT = {
   "BACTERIA": dict(adj_T=lambda s: [s.params[3]], rows=[-1]),  # adj_T = [C] (bacteria.py:49)
   "PREDATORPREY": dict(adj_T=[1.0, 0.0, 0.0], rows=[-1]),      # predator_prey.py:68
   "BEARPOPULATIONS": dict(adj_T=None, rows=[-2, -1]),
+  "INVASIVEPLANT": dict(adj_T=[1.0] * 5, rows=[-1] * 5),  # discrete; every control clamps with the last row (invasive_plant.py:90)
 }
 
 
@@ -59,13 +60,15 @@ class FBSM(IndirectMethodOptimizer):
   def __init__(self, hp: HParams, cfg: Config, system) -> None:
     self.hp, self.cfg, self.system = hp, cfg, system
     name = getattr(system, "device_name", "")
-    if getattr(system, "discrete", False):
-      raise NotImplementedError("discrete systems (INVASIVEPLANT) have no device implementation")
     if name not in INDIRECT:
       raise NotImplementedError(f"system {name or type(system).__name__} has no adj_ODE / optim_characterization: "
                                 "FBSM needs an indirect (Lenhart) system")
     self.N = int(hp.fbsm_intervals)
     self.h = float(system.T) / self.N
+    self.discrete = bool(getattr(system, "discrete", False))
+    if self.discrete:  # forward_backward_sweep.py:33-35
+      self.N, self.h = int(system.T), 1
+    self.u_rows = self.N if self.discrete else self.N + 1
     n, m = system.state_size, system.control_size
     info = INDIRECT[name]
     adj_T = info["adj_T"](system) if callable(info["adj_T"]) else info["adj_T"]
@@ -75,7 +78,7 @@ class FBSM(IndirectMethodOptimizer):
     self.char_ub = np.ascontiguousarray(b[info["rows"], 1])
     # the reference's guesses (forward_backward_sweep.py:40-50), kept as attributes like there
     self.x_guess = np.vstack((np.asarray(system.x_0, dtype=np.float64), np.zeros((self.N, n))))
-    self.u_guess = np.zeros((self.N + 1, m))
+    self.u_guess = np.zeros((self.u_rows, m))
     self.adj_guess = np.zeros((self.N + 1, n)) if self.adj_T is None else np.vstack((np.zeros((self.N, n)), self.adj_T))
     self.t_interval = np.linspace(0, system.T, num=self.N + 1).reshape(-1, 1)
     self.guess = np.concatenate([self.x_guess.ravel(), self.u_guess.ravel(), self.adj_guess.ravel()])
@@ -105,7 +108,7 @@ class FBSM(IndirectMethodOptimizer):
 
   def solve_batch(self, x0, device=None) -> Dict[str, torch.Tensor]:
     """x0: (B, n) start states (host or device).  Returns device tensors x, adj: (B, N+1, n), u: (B, N+1, m) (views of the
-    kernel's time-major storage), iters, status: (B,)."""
+    kernel's time-major storage; N rows of u for a discrete system), iters, status: (B,)."""
     if not torch.cuda.is_available():
       raise ML.MyriadError("FBSM.solve_batch runs the CUDA sweep kernel: a CUDA device is required (no CPU fallback)")
     dev = torch.device(device or "cuda")
@@ -114,7 +117,7 @@ class FBSM(IndirectMethodOptimizer):
     x0 = x0.reshape(-1, n).to(dev, non_blocking=True).contiguous()
     B = x0.shape[0]
     x = torch.empty(self.N + 1, n, B, dtype=torch.float64, device=dev)
-    u = torch.empty(self.N + 1, m, B, dtype=torch.float64, device=dev)
+    u = torch.empty(self.u_rows, m, B, dtype=torch.float64, device=dev)
     adj = torch.empty(self.N + 1, n, B, dtype=torch.float64, device=dev)
     iters = torch.empty(B, dtype=torch.int32, device=dev)
     status = torch.empty(B, dtype=torch.int32, device=dev)
@@ -135,7 +138,7 @@ class FBSM(IndirectMethodOptimizer):
     x0 = torch.as_tensor(np.asarray(x0, dtype=np.float64)).reshape(-1, n).contiguous()
     B = x0.shape[0]
     x = torch.empty(self.N + 1, n, B, dtype=torch.float64)
-    u = torch.empty(self.N + 1, m, B, dtype=torch.float64)
+    u = torch.empty(self.u_rows, m, B, dtype=torch.float64)
     adj = torch.empty(self.N + 1, n, B, dtype=torch.float64)
     iters = torch.empty(B, dtype=torch.int32)
     status = torch.empty(B, dtype=torch.int32)

@@ -5,7 +5,7 @@ Follows, line for line in meaning:
   * FBSM.solve / sequencesolver / reinitiate   myriad/trajectory_optimizers/forward_backward_sweep.py:75-158
   * integrate_fbsm (RK4, both directions)      myriad/utils.py:138-197
   * stopping_criterion                         myriad/trajectory_optimizers/base.py:128-141
-  * dynamics / adj_ODE / optim_characterization of the 13 continuous Lenhart systems  myriad/systems/lenhart/*.py
+  * dynamics / adj_ODE / optim_characterization of the 14 indirect Lenhart systems  myriad/systems/lenhart/*.py
 Pinned: tests/test_fbsm.py checks it against tests/golden/fbsm_*.npz, which oracle/make_fbsm_golden.py produced by
 running the unmodified reference under oracle/refshim.
 """
@@ -138,6 +138,14 @@ def _bear_opt(a, x, t, p, b):  # bear_populations.py:129-139
 
 SYSTEMS["BEARPOPULATIONS"].update(f=_bear_f, adj=_bear_adj, opt=_bear_opt)
 
+# invasive_plant.py:38-90 -- DISCRETE: f is the next state, adj the previous adjoint, opt one row of the shifted rule
+SYSTEMS["INVASIVEPLANT"] = dict(
+  T=10., x_0=[.5, 1., 1.5, 2., 10.], bounds=[[-INF, INF]] * 5 + [[0., 1.]] * 5, adj_T=[1.] * 5, discrete=True,
+  p=dict(B=1., k=1., eps=.01),
+  f=lambda x, u, t, p: (x + x * p["k"] / (p["eps"] + x)) * (1 - u),
+  adj=lambda a, x, u, t, p: a * (1 - u) * (1 + p["eps"] * p["k"] / (p["eps"] + x) ** 2),
+  opt=lambda a, x, t, p, b: clamp(0.5 * a / p["B"] * (x + x * p["k"] / (p["eps"] + x)), b[-1, 0], b[-1, 1]))
+
 
 def _rk4(fn, y, a0, a1, b0, b1, t, h):
   """rk4_step of integrate_fbsm (utils.py:166-176): fn(y, a, b, t)"""
@@ -156,6 +164,9 @@ def solve(name: str, N: int, x_0=None, max_iter: int = 10000):
   b = np.asarray(S["bounds"], dtype=np.float64)
   x_0 = np.asarray(S["x_0"] if x_0 is None else x_0, dtype=np.float64)
   n, m = x_0.shape[0], b.shape[0] - x_0.shape[0]
+  discrete = bool(S.get("discrete"))
+  if discrete:  # forward_backward_sweep.py:33-35
+    N = int(T)
   h = T / N
   ts = np.linspace(0, T, N + 1)
   f = lambda x, u, _v, t: np.atleast_1d(S["f"](x, u, t, p))
@@ -166,12 +177,19 @@ def solve(name: str, N: int, x_0=None, max_iter: int = 10000):
     while True:
       old_x, old_u, old_adj = x.copy(), u.copy(), adj.copy()
       x = x.copy()
-      for i in range(N):  # forward (utils.py:190-192)
-        x[i + 1] = _rk4(f, x[i], u[i], u[i + 1], 0.0, 0.0, ts[i], h)
       adj = adj.copy()
-      for i in range(N, 0, -1):  # backward (utils.py:194-196)
-        adj[i - 1] = _rk4(g, adj[i], x[i], x[i - 1], u[i], u[i - 1], ts[i], -h)
-      est = np.stack([np.atleast_1d(S["opt"](adj[i], x[i], ts[i], p, b)) for i in range(N + 1)])
+      if discrete:  # utils.py:182-186: direct evaluation, no integration
+        for i in range(N):
+          x[i + 1] = f(x[i], u[i], None, ts[i])
+        for i in range(N, 0, -1):
+          adj[i - 1] = g(adj[i], x[i], u[i - 1], ts[i - 1])
+        est = np.stack([np.atleast_1d(S["opt"](adj[i + 1], x[i], ts[i], p, b)) for i in range(N)])  # shifted rows
+      else:
+        for i in range(N):  # forward (utils.py:190-192)
+          x[i + 1] = _rk4(f, x[i], u[i], u[i + 1], 0.0, 0.0, ts[i], h)
+        for i in range(N, 0, -1):  # backward (utils.py:194-196)
+          adj[i - 1] = _rk4(g, adj[i], x[i], x[i - 1], u[i], u[i - 1], ts[i], -h)
+        est = np.stack([np.atleast_1d(S["opt"](adj[i], x[i], ts[i], p, b)) for i in range(N + 1)])
       u = 0.5 * (est + old_u)
       sweeps[0] += 1
       sx = np.abs(x).sum(0) * 1e-3 - np.abs(x - old_x).sum(0)
@@ -182,7 +200,7 @@ def solve(name: str, N: int, x_0=None, max_iter: int = 10000):
 
   def guesses(a=None, ts_idx=None):
     x = np.vstack((x_0, np.zeros((N, n))))
-    u = np.zeros((N + 1, m))
+    u = np.zeros((N if discrete else N + 1, m))
     adj = np.zeros((N + 1, n))
     if S.get("adj_T") is not None:
       adj[-1] = S["adj_T"]

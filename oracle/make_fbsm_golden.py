@@ -24,6 +24,7 @@ CASES = {
   "SIMPLECASE": (1000, 2), "SIMPLECASEWITHBOUNDS": (200, 2), "CANCERTREATMENT": (1000, 2), "MOULDFUNGICIDE": (200, 1),
   "BIOREACTOR": (200, 2), "GLUCOSE": (200, 2), "HARVEST": (200, 2), "TIMBERHARVEST": (200, 1), "EPIDEMICSEIRN": (200, 1),
   "HIVTREATMENT": (200, 1), "BACTERIA": (200, 1), "PREDATORPREY": (200, 0), "BEARPOPULATIONS": (200, 1),
+  "INVASIVEPLANT": (10, 2),  # discrete: N = int(T) whatever fbsm_intervals says (forward_backward_sweep.py:33-35)
 }
 
 

@@ -44,8 +44,8 @@ def test_system_descriptors_match_reference_tables():
   assert ct.x_T is None and ct.T == 20 and np.allclose(ct.x_0, [0.975])
   rl = SystemType.ROCKETLANDING()
   assert rl.state_size == 6 and rl.control_size == 2 and rl.T == 16.0
-  with pytest.raises(NotImplementedError):   # discrete system: rejected like in the reference (base.py:66-67)
-    SystemType.INVASIVEPLANT()
+  ip = SystemType.INVASIVEPLANT()   # discrete system: FBSM only; the direct optimizers reject it like the reference (base.py:66-67)
+  assert ip.discrete and ip.state_size == 5 and ip.control_size == 5 and ip.T == 10.0
 
 
 def test_shard_ranges_cover_everything():

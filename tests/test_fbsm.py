@@ -1,7 +1,7 @@
 """Forward-Backward Sweep Method (myriad/trajectory_optimizers/forward_backward_sweep.py) parity.
 
-tests/golden/fbsm_*.npz hold the UNMODIFIED reference's {'x', 'u', 'adj'} and its sweep counts for the 13 continuous Lenhart
-systems (oracle/make_fbsm_golden.py, reference run under oracle/refshim).  CPU tests pin the NumPy restatement
+tests/golden/fbsm_*.npz hold the UNMODIFIED reference's {'x', 'u', 'adj'} and its sweep counts for the 14 indirect (Lenhart)
+systems, the discrete INVASIVEPLANT included (oracle/make_fbsm_golden.py, reference run under oracle/refshim).  CPU tests pin the NumPy restatement
 (oracle/fbsm.py) and the host build of the sweep templates to them; the GPU tests run the product path
 (get_optimizer(...).solve_batch -> myr_fbsm_solve) against the fixtures and, for random start states, against the oracle.
 
@@ -120,7 +120,7 @@ def test_gpu_fbsm_matches_reference_fixture(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,N,B", [("CANCERTREATMENT", 1000, 4096), ("HIVTREATMENT", 200, 1000), ("BEARPOPULATIONS", 100, 777),
-                                      ("PREDATORPREY", 100, 65)])
+                                      ("PREDATORPREY", 100, 65), ("INVASIVEPLANT", 10, 333)])
 def test_gpu_fbsm_random_start_states_against_oracle(name, N, B):
   """ragged batch sizes; a sample of rows is re-solved by the NumPy oracle; whole-batch properties for the rest"""
   opt = _optimizer(name, N)
