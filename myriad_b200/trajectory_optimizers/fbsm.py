@@ -145,3 +145,24 @@ class FBSM(IndirectMethodOptimizer):
     self._call(ML.lib().myr_host_fbsm_solve, x0, x, u, adj, iters, status)
     return {"x": x.permute(2, 0, 1).numpy(), "u": u.permute(2, 0, 1).numpy(), "adj": adj.permute(2, 0, 1).numpy(),
             "iters": iters.numpy(), "status": status.numpy()}
+
+  def solve_batch_sharded(self, x0_all, host: bool = False) -> Dict[str, torch.Tensor]:
+    """One process per GPU: this rank solves its contiguous share of the start states (myriad_b200.distributed.shard_range)
+    and ONE all_gather hands every rank all trajectories in global row order.  Instances are independent, so there is no
+    data-path collective.  ``host=True`` uses the host build (CPU CI with the gloo backend)."""
+    from myriad_b200 import distributed as D
+    rank, world, _ = D.world()
+    n, m = self.system.state_size, self.system.control_size
+    x0_all = torch.as_tensor(np.asarray(x0_all, dtype=np.float64) if not torch.is_tensor(x0_all) else x0_all).reshape(-1, n)
+    lo, hi = D.shard_range(x0_all.shape[0], rank, world)
+    r = self.host_solve_batch(x0_all[lo:hi].cpu().numpy()) if host else self.solve_batch(x0_all[lo:hi])
+    t = lambda a: torch.as_tensor(a)
+    B = hi - lo
+    packed = torch.cat([t(r["x"]).reshape(B, -1), t(r["u"]).reshape(B, -1), t(r["adj"]).reshape(B, -1),
+                        t(r["iters"]).double()[:, None], t(r["status"]).double()[:, None]], dim=1).contiguous()
+    allp = D.gather_solutions(packed)
+    nx, nu = (self.N + 1) * n, self.u_rows * m
+    Bt = allp.shape[0]
+    return {"x": allp[:, :nx].reshape(Bt, self.N + 1, n), "u": allp[:, nx:nx + nu].reshape(Bt, self.u_rows, m),
+            "adj": allp[:, nx + nu:nx + nu + nx].reshape(Bt, self.N + 1, n), "iters": allp[:, -2].to(torch.int32),
+            "status": allp[:, -1].to(torch.int32)}

@@ -99,6 +99,41 @@ def test_host_empty_batch_and_unsupported_system():
   assert rc == -2 and b"adj_ODE" in ML.lib().myr_last_error()
 
 
+def _gloo_fbsm_worker(rank, world, port, q):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+  import torch.distributed as dist
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  opt = _optimizer("CANCERTREATMENT", 60)
+  r = opt.solve_batch_sharded(_five_starts(), host=True)  # UNEQUAL shards: 3 + 2
+  if rank == 0:
+    q.put({k: v.numpy() for k, v in r.items()})
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def _five_starts():
+  return 0.975 * (1.0 + 0.05 * np.linspace(-1, 1, 5))[:, None]
+
+
+def test_two_rank_sharded_fbsm_gloo():
+  """world_size 2 on CPU (gloo): shard the start states by rows, sweep independently, one all_gather"""
+  import torch.multiprocessing as mp
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 29500 + (os.getpid() % 2000)
+  procs = [ctx.Process(target=_gloo_fbsm_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  got = q.get(timeout=300)
+  for p in procs:
+    p.join(timeout=120)
+    assert p.exitcode == 0
+  want = _optimizer("CANCERTREATMENT", 60).host_solve_batch(_five_starts())
+  for k in ("x", "u", "adj", "iters", "status"):
+    assert got[k].shape == want[k].shape, k
+    assert np.array_equal(got[k], want[k]), k
+
+
 # ------------------------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", SYSTEMS)
