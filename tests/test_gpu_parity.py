@@ -249,6 +249,26 @@ def test_full_size_batches_satisfy_their_own_kkt_conditions(case, B):
   assert bool((z >= lb[ok] - 1e-8 * (1 + lb[ok].abs())).all()) and bool((z <= ub[ok] + 1e-8 * (1 + ub[ok].abs())).all())
 
 
+def test_node_hermite_simpson_full_size_fits_shared_memory_plan():
+  """NODE dynamics + Hermite-Simpson at N=100 (CR scratch + MLP scratch + staged weights exceed one CTA's shared
+  memory): the slot plan must spill to the workspace instead of failing the launch, and the solve must satisfy its own
+  KKT conditions."""
+  from myriad_b200 import problems as PR
+  from tests.cases import product_system
+  tr = PR.Transcription(product_system("NODE_CARTPOLE"), PR.HERMITE_SIMPSON, "RK4", 100, 1)
+  eng = _eng(tr)
+  x0, z0, lb, ub = _batch(tr, 8)
+  out = eng.ipm_solve(z0, lb, ub)
+  torch.cuda.synchronize()
+  ok = out["status"] == 0
+  assert int(ok.sum()) >= 7, out["status"]
+  assert float(out["con_inf"][ok].max()) <= 1e-8
+  r = eng.eval(out["z"])
+  torch.cuda.synchronize()
+  np.testing.assert_allclose(r.f[ok].cpu().numpy(), out["obj"][ok].cpu().numpy(), rtol=1e-10, atol=1e-12)
+  assert float(r.c.abs().max(dim=1).values[ok].max()) <= 1e-8
+
+
 def test_empty_batch_and_bad_arguments():
   from myriad_b200 import _lib as ML
   tr = _tr("s_cartpole_trap_10")
