@@ -312,7 +312,8 @@ __global__ void __launch_bounds__(EvalLaunch<S>::kThreads, EvalLaunch<S>::kMinBl
   double* sphi = smem + 64;
   double* spsi = sphi + Q * NC;
   double* sJ = spsi + Q * NC;             // St * ROWP
-  double* sH = sJ + (size_t)St * ROWP;    // Q * NWP (only when the Hessian is requested)
+  double* sH = sJ + (J_out ? (size_t)St * ROWP : 0);  // Q * NWP (only when the Hessian is requested); the Jacobian rows are
+                                                       // staged only when asked for -- same rule as the launch's size
   const bool want_h = lam_all && H_out;
   // NODE systems: per-node MLP outputs + the tensor-core pass's scratch live behind the other regions
   double* sDyn = sH + ((lam_all && H_out) ? (size_t)Q * S::NWP : 0);

@@ -54,7 +54,11 @@ class Engine:
       self.jblk_shape = (s.stages, s.stage_nodes, s.nc, s.nw)
 
   # ---- K1
-  def eval(self, z: torch.Tensor, lam: Optional[torch.Tensor] = None, hessian: bool = False, out: Optional[EvalResult] = None) -> EvalResult:
+  def eval(self, z: torch.Tensor, lam: Optional[torch.Tensor] = None, hessian: bool = False, out: Optional[EvalResult] = None,
+           jac: bool = True) -> EvalResult:
+    """jac=False: objective and constraints only (grad / Jblk are None).  The stand-alone K1 stages an instance's whole block
+    Jacobian in shared memory; the one configuration where that does not fit (NODE dynamics + Hermite-Simpson at N ~ 100:
+    myr_eval returns MYR_E_UNSUPPORTED -> NotImplementedError) still evaluates f and c this way."""
     _need_cuda(z, lam)
     s = self.sizes
     B = z.shape[0]
@@ -63,14 +67,14 @@ class Engine:
     if out is None:
       out = EvalResult(
         f=torch.empty(B, dtype=torch.float64, device=dev),
-        grad=torch.empty(B, s.nvars, dtype=torch.float64, device=dev),
+        grad=torch.empty(B, s.nvars, dtype=torch.float64, device=dev) if jac else None,
         c=torch.empty(B, s.ncon, dtype=torch.float64, device=dev),
-        Jblk=torch.empty((B,) + self.jblk_shape, dtype=torch.float64, device=dev),
+        Jblk=torch.empty((B,) + self.jblk_shape, dtype=torch.float64, device=dev) if jac else None,
         Hblk=torch.empty(B, s.nodes, s.nw * (s.nw + 1) // 2, dtype=torch.float64, device=dev) if hessian else None)
     if hessian and lam is None:
       lam = torch.zeros(B, s.ncon, dtype=torch.float64, device=dev)
-    ML.check(ML.lib().myr_eval(C.byref(self.desc), B, _ptr(z), _ptr(lam), _ptr(out.f), _ptr(out.grad), _ptr(out.c),
-                               _ptr(out.Jblk), _ptr(out.Hblk) if hessian else None, _stream()))
+    ML.check(ML.lib().myr_eval(C.byref(self.desc), B, _ptr(z), _ptr(lam), _ptr(out.f), _ptr(out.grad) if jac else None, _ptr(out.c),
+                               _ptr(out.Jblk) if jac else None, _ptr(out.Hblk) if hessian else None, _stream()))
     return out
 
   def jtvec(self, Jblk: torch.Tensor, lam: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

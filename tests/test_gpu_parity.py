@@ -263,7 +263,11 @@ def test_node_hermite_simpson_full_size_fits_shared_memory_plan():
   ok = out["status"] == 0
   assert int(ok.sum()) >= 7, out["status"]
   assert float(out["con_inf"][ok].max()) <= 1e-8
-  r = eng.eval(out["z"])
+  # the stand-alone K1 stages an instance's whole block Jacobian in shared memory: at this size that does not fit and
+  # the call says so (the IPM kernel evaluates node by node and is not affected); f and c alone still evaluate
+  with pytest.raises(NotImplementedError, match="too large for the shared-memory staged K1"):
+    eng.eval(out["z"])
+  r = eng.eval(out["z"], jac=False)
   torch.cuda.synchronize()
   np.testing.assert_allclose(r.f[ok].cpu().numpy(), out["obj"][ok].cpu().numpy(), rtol=1e-10, atol=1e-12)
   assert float(r.c.abs().max(dim=1).values[ok].max()) <= 1e-8
