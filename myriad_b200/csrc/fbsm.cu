@@ -14,9 +14,12 @@ double system_default_T(int id);                                           // ap
 // One warp per CTA: a warp is the unit that runs until its slowest instance has converged, registers (not the CTA count)
 // bound the occupancy, and 32-thread CTAs spread a small batch over 4x as many SMs as 128-thread ones would.
 constexpr int kFbsmThreads = 32;
+#ifndef MYR_FBSM_MIN_CTAS
+#define MYR_FBSM_MIN_CTAS 1  // resident CTAs per SM the register allocation must allow (A/B knob)
+#endif
 
 template <class Sys>
-__global__ void __launch_bounds__(kFbsmThreads) fbsm_kernel(const __grid_constant__ FbsmParams P) {
+__global__ void __launch_bounds__(kFbsmThreads, MYR_FBSM_MIN_CTAS) fbsm_kernel(const __grid_constant__ FbsmParams P) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
   FbsmInstance<Sys>(P, b).run();
